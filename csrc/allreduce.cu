@@ -1,0 +1,283 @@
+// Fused gradient all-reduce over NVLink peer memory (K-AR) -- no NCCL on this path.
+//
+// What the reference gets from DDP's Reducer + a gloo ring (distributedVggf.py:225):
+// grad <- (1/ws) * sum over ranks, per bucket, overlapped with the rest of backward.  Here one
+// kernel per bucket does, on a side stream while backward keeps running:
+//
+//   pack     wire[i] = bf16(grad_f32[i] * 1/ws)            local fp32 arena -> symmetric wire
+//   barrier  CTA b of every rank handshakes with CTA b of every peer (flags in peer memory,
+//            st.release.sys / ld.acquire.sys); CTAs never wait for other CTAs of the same GPU
+//   reduce   one-shot : every rank loads chunk b from all peers, sums in fp32, keeps it locally
+//            two-shot : rank r loads its 1/ws sub-slice of chunk b from all peers, sums in fp32,
+//                       and pushes the bf16 result into every peer's wire (reduce-scatter +
+//                       all-gather in one pass, 2(ws-1)/ws bytes per element on the wire)
+//            NVLS     : rank r issues multimem.ld_reduce (the switch adds the ws copies with fp32
+//                       accumulation) on its sub-slice and multimem.st broadcasts the result
+//   barrier  everybody is done reading / writing my wire
+//   unpack   optional fp32 write-back into the arena (the fused Adam can read the bf16 wire
+//            directly instead)
+//
+// Work decomposition: the bucket is cut into G chunks (one per CTA), each chunk into `world`
+// cells; cell (b, r) is reduced by CTA b of rank r.  A chunk is only ever touched by the CTAs
+// with the same index, which is what makes the per-CTA handshake sufficient.
+#include <stdexcept>
+
+#include "api.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int AR_MAX_CTAS = 64;
+constexpr int AR_MAX_WORLD = 16;
+constexpr int AR_THREADS = 512;
+constexpr int AR_SLOT_WORDS = 2 * AR_MAX_CTAS * AR_MAX_WORLD;   // two phases per slot
+
+__device__ __forceinline__ uint32_t* flag_ptr(uint32_t* pad, int slot, int phase, int cta, int src) {
+  return pad + ((static_cast<long long>(slot) * 2 + phase) * AR_MAX_CTAS + cta) * AR_MAX_WORLD + src;
+}
+
+// Handshake between the CTAs with index `cta` on all ranks.  Thread t < world talks to peer t.
+__device__ __forceinline__ void cta_barrier_all_ranks(const CommCtx& c, int slot, int phase, int cta,
+                                                      uint32_t epoch) {
+  __syncthreads();
+  if (threadIdx.x < c.world) {
+    const int peer = threadIdx.x;
+    fence_acq_rel_sys();
+    st_release_sys(flag_ptr(c.signal_ptrs[peer], slot, phase, cta, c.rank), epoch);
+    const uint32_t* mine = flag_ptr(c.signal_ptrs[c.rank], slot, phase, cta, peer);
+    unsigned long long spins = 0;
+    while (static_cast<int>(ld_acquire_sys(mine) - epoch) < 0) {
+      if (++spins > (1ull << 25)) {
+        printf("[b200] cross-GPU barrier timeout rank=%d peer=%d slot=%d phase=%d cta=%d epoch=%u seen=%u\n",
+               c.rank, peer, slot, phase, cta, epoch, ld_relaxed_sys(mine));
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ uint4 ld_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void accum_bf16x8(float (&acc)[8], const uint4& v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = unpack_bf16x2(w[i]);
+    acc[2 * i] += f.x;
+    acc[2 * i + 1] += f.y;
+  }
+}
+
+struct ArArgs {
+  CommCtx c;
+  const float* grad;       // local fp32 arena (nullptr: wire already holds the packed data)
+  float* grad_out;         // optional fp32 write-back
+  long long start;         // element offset of the bucket inside arena and wire
+  long long n;             // elements (multiple of 8)
+  float inv_world;
+  int slot;
+  uint32_t epoch;
+};
+
+// One 16-byte wire vector = 8 bf16 (WIRE32 = false) or 4 fp32 (WIRE32 = true).
+template <int ALGO, bool WIRE32>
+__global__ void __launch_bounds__(AR_THREADS, 1) allreduce_kernel(const ArArgs a) {
+  constexpr int EPV = WIRE32 ? 4 : 8;                 // elements per vector
+  const CommCtx& c = a.c;
+  const int b = blockIdx.x, G = gridDim.x, world = c.world, rank = c.rank;
+  const long long nvec = a.n / EPV;
+  const long long cell = (nvec + static_cast<long long>(G) * world - 1) / (static_cast<long long>(G) * world);
+  const long long chunk0 = min(nvec, static_cast<long long>(b) * world * cell);
+  const long long chunk1 = min(nvec, static_cast<long long>(b + 1) * world * cell);
+  uint8_t* my_wire = reinterpret_cast<uint8_t*>(c.wire_ptrs[rank]) + a.start * (WIRE32 ? 4 : 2);
+
+  // ---- pack: fp32 arena -> wire (scaled, rounded once) -----------------------------------------
+  if (a.grad) {
+    const float* g = a.grad + a.start;
+    for (long long v = chunk0 + threadIdx.x; v < chunk1; v += AR_THREADS) {
+      if constexpr (WIRE32) {
+        float4 x = *reinterpret_cast<const float4*>(g + v * 4);
+        x.x *= a.inv_world; x.y *= a.inv_world; x.z *= a.inv_world; x.w *= a.inv_world;
+        *reinterpret_cast<float4*>(my_wire + v * 16) = x;
+      } else {
+        const float4 x0 = *reinterpret_cast<const float4*>(g + v * 8);
+        const float4 x1 = *reinterpret_cast<const float4*>(g + v * 8 + 4);
+        const float s = a.inv_world;
+        st_v4(my_wire + v * 16, make_uint4(pack_bf16x2(x0.x * s, x0.y * s), pack_bf16x2(x0.z * s, x0.w * s),
+                                           pack_bf16x2(x1.x * s, x1.y * s), pack_bf16x2(x1.z * s, x1.w * s)));
+      }
+    }
+  }
+  cta_barrier_all_ranks(c, a.slot, 0, b, a.epoch);
+
+  // ---- reduce ---------------------------------------------------------------------------------
+  if constexpr (ALGO == AR_ONESHOT) {
+    // every rank reduces the whole chunk; result goes to the local fp32 arena (never to the wire,
+    // which peers are still reading).
+    float* out = a.grad_out + a.start;
+    for (long long v = chunk0 + threadIdx.x; v < chunk1; v += AR_THREADS) {
+      if constexpr (WIRE32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < world; ++p) {
+          const int peer = (rank + p) % world;
+          const uint4 raw = ld_v4(reinterpret_cast<const uint8_t*>(c.wire_ptrs[peer]) + a.start * 4 + v * 16);
+          acc.x += __uint_as_float(raw.x); acc.y += __uint_as_float(raw.y);
+          acc.z += __uint_as_float(raw.z); acc.w += __uint_as_float(raw.w);
+        }
+        *reinterpret_cast<float4*>(out + v * 4) = acc;
+      } else {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int p = 0; p < world; ++p) {
+          const int peer = (rank + p) % world;
+          accum_bf16x8(acc, ld_v4(reinterpret_cast<const uint8_t*>(c.wire_ptrs[peer]) + a.start * 2 + v * 16));
+        }
+        *reinterpret_cast<float4*>(out + v * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(out + v * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+    }
+    cta_barrier_all_ranks(c, a.slot, 1, b, a.epoch);
+    return;
+  }
+
+  const long long cell0 = min(chunk1, chunk0 + static_cast<long long>(rank) * cell);
+  const long long cell1 = min(chunk1, cell0 + cell);
+  if constexpr (ALGO == AR_TWOSHOT) {
+    for (long long v = cell0 + threadIdx.x; v < cell1; v += AR_THREADS) {
+      const long long boff = a.start * (WIRE32 ? 4 : 2) + v * 16;
+      uint4 res;
+      if constexpr (WIRE32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < world; ++p) {
+          const int peer = (rank + p) % world;
+          const uint4 raw = ld_v4(reinterpret_cast<const uint8_t*>(c.wire_ptrs[peer]) + boff);
+          acc.x += __uint_as_float(raw.x); acc.y += __uint_as_float(raw.y);
+          acc.z += __uint_as_float(raw.z); acc.w += __uint_as_float(raw.w);
+        }
+        res = make_uint4(__float_as_uint(acc.x), __float_as_uint(acc.y), __float_as_uint(acc.z), __float_as_uint(acc.w));
+      } else {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int p = 0; p < world; ++p) {
+          const int peer = (rank + p) % world;
+          accum_bf16x8(acc, ld_v4(reinterpret_cast<const uint8_t*>(c.wire_ptrs[peer]) + boff));
+        }
+        res = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                         pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+      }
+      for (int p = 0; p < world; ++p) {
+        const int peer = (rank + p) % world;
+        st_v4(reinterpret_cast<uint8_t*>(c.wire_ptrs[peer]) + boff, res);
+      }
+    }
+  } else {   // AR_NVLS: the switch reduces and broadcasts
+    uint8_t* mc = reinterpret_cast<uint8_t*>(c.wire_mc) + a.start * (WIRE32 ? 4 : 2);
+    for (long long v = cell0 + threadIdx.x; v < cell1; v += AR_THREADS) {
+      if constexpr (WIRE32) {
+        const float4 r = multimem_ld_reduce_f32x4(mc + v * 16);
+        multimem_st_v4(mc + v * 16, make_uint4(__float_as_uint(r.x), __float_as_uint(r.y),
+                                               __float_as_uint(r.z), __float_as_uint(r.w)));
+      } else {
+        multimem_st_v4(mc + v * 16, multimem_ld_reduce_bf16x8(mc + v * 16));
+      }
+    }
+  }
+  cta_barrier_all_ranks(c, a.slot, 1, b, a.epoch);
+
+  // ---- unpack (optional): wire -> fp32 arena ----------------------------------------------------
+  if (a.grad_out) {
+    float* out = a.grad_out + a.start;
+    for (long long v = chunk0 + threadIdx.x; v < chunk1; v += AR_THREADS) {
+      const uint4 raw = ld_v4(my_wire + v * 16);
+      if constexpr (WIRE32) {
+        *reinterpret_cast<uint4*>(out + v * 4) = raw;
+      } else {
+        const float2 f0 = unpack_bf16x2(raw.x), f1 = unpack_bf16x2(raw.y), f2 = unpack_bf16x2(raw.z),
+                     f3 = unpack_bf16x2(raw.w);
+        *reinterpret_cast<float4*>(out + v * 8) = make_float4(f0.x, f0.y, f1.x, f1.y);
+        *reinterpret_cast<float4*>(out + v * 8 + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+      }
+    }
+  }
+}
+
+void allreduce_fused(const CommCtx& ctx, const float* grad_f32, float* grad_out_f32, long long start,
+                     long long n, float inv_world, int algo, bool wire_fp32, int slot, uint32_t epoch,
+                     int max_ctas, cudaStream_t s) {
+  if (ctx.world > AR_MAX_WORLD) throw std::runtime_error("[b200] allreduce_fused: world too large");
+  if (n % 8 || start % 8) throw std::runtime_error("[b200] allreduce_fused: range must be 8-element aligned");
+  if (algo == AR_ONESHOT && !grad_out_f32)
+    throw std::runtime_error("[b200] allreduce_fused: one-shot needs an fp32 output");
+  if (algo == AR_NVLS && !ctx.wire_mc)
+    throw std::runtime_error("[b200] allreduce_fused: NVLS requested but no multicast mapping");
+  ArArgs a;
+  a.c = ctx; a.grad = grad_f32; a.grad_out = grad_out_f32; a.start = start; a.n = n;
+  a.inv_world = inv_world; a.slot = slot; a.epoch = epoch;
+  const int epv = wire_fp32 ? 4 : 8;
+  const long long nvec = n / epv;
+  int G = max_ctas <= 0 ? 16 : max_ctas;
+  if (G > AR_MAX_CTAS) G = AR_MAX_CTAS;
+  // at least ~2 vectors per thread per cell, otherwise fewer CTAs (latency-bound small buckets)
+  long long want = nvec / (static_cast<long long>(AR_THREADS) * ctx.world) + 1;
+  if (want < G) G = static_cast<int>(want);
+  if (G < 1) G = 1;
+#define AR_LAUNCH(ALGO)                                                           \
+  if (wire_fp32) allreduce_kernel<ALGO, true><<<G, AR_THREADS, 0, s>>>(a);        \
+  else allreduce_kernel<ALGO, false><<<G, AR_THREADS, 0, s>>>(a);
+  switch (algo) {
+    case AR_ONESHOT: AR_LAUNCH(AR_ONESHOT) break;
+    case AR_TWOSHOT: AR_LAUNCH(AR_TWOSHOT) break;
+    case AR_NVLS: AR_LAUNCH(AR_NVLS) break;
+    default: throw std::runtime_error("[b200] allreduce_fused: unknown algorithm");
+  }
+#undef AR_LAUNCH
+  count_launch();
+  check_last("allreduce_fused");
+}
+
+// ------------------------------------------------------------------------------------ broadcast
+// K-BCAST (DDP's constructor sync, distributedVggf.py:225): root stages fp32 data in its wire
+// buffer, everybody pulls it over NVLink.  Called on chunks that fit the wire buffer.
+__global__ void __launch_bounds__(AR_THREADS, 1)
+broadcast_kernel(const CommCtx c, float* data, long long n, int root, int slot, uint32_t epoch) {
+  const int b = blockIdx.x, G = gridDim.x;
+  const long long nvec = n / 4;
+  const long long per = (nvec + G - 1) / G;
+  const long long v0 = min(nvec, b * per), v1 = min(nvec, v0 + per);
+  uint8_t* root_wire = reinterpret_cast<uint8_t*>(c.wire_ptrs[root]);
+  if (c.rank == root)
+    for (long long v = v0 + threadIdx.x; v < v1; v += AR_THREADS)
+      st_v4(root_wire + v * 16, *reinterpret_cast<const uint4*>(data + v * 4));
+  cta_barrier_all_ranks(c, slot, 0, b, epoch);
+  if (c.rank != root)
+    for (long long v = v0 + threadIdx.x; v < v1; v += AR_THREADS)
+      *reinterpret_cast<uint4*>(data + v * 4) = ld_v4(root_wire + v * 16);
+  cta_barrier_all_ranks(c, slot, 1, b, epoch);
+}
+
+void broadcast_fused(const CommCtx& ctx, float* data_f32, long long n, int root, int slot,
+                     uint32_t epoch, cudaStream_t s) {
+  if (n % 4) throw std::runtime_error("[b200] broadcast_fused: n must be a multiple of 4");
+  broadcast_kernel<<<32, AR_THREADS, 0, s>>>(ctx, data_f32, n, root, slot, epoch);
+  count_launch();
+  check_last("broadcast_fused");
+}
+
+__global__ void barrier_kernel(const CommCtx c, int slot, uint32_t epoch) {
+  cta_barrier_all_ranks(c, slot, 0, 0, epoch);
+}
+void device_barrier(const CommCtx& ctx, int slot, uint32_t epoch, cudaStream_t s) {
+  barrier_kernel<<<1, 32, 0, s>>>(ctx, slot, epoch);
+  count_launch();
+  check_last("device_barrier");
+}
+
+int allreduce_signal_words(int slots) { return slots * AR_SLOT_WORDS; }
+
+}  // namespace b200

@@ -1,0 +1,328 @@
+// Policies for umma_core.cuh: where each k-block's operand tiles come from and what happens to
+// the accumulator.  Three families:
+//   GemmPolicy   2-D operands (FC fwd / dgrad / wgrad, layer-0 im2col GEMM), optional split-K.
+//   ConvPolicy   3x3/s1/p1 convolution as implicit GEMM: the A tile of tap (kh,kw) is a 4-D TMA
+//                box of the NHWC activation shifted by (kh-1, kw-1); TMA's out-of-bounds zero fill
+//                *is* the padding.  fprop: B = W[Cout][9*Cin] K-major.  dgrad: the same weight
+//                tensor read MN-major with the taps mirrored (no transposed weight copy).
+//   WgradPolicy  dW[cout][tap][cin] = sum_pixels dZ[p][cout] * X[p+tap][cin]: both operands are
+//                MN-major 4-D boxes (K = 64 pixels per k-block), split-K over pixel tiles,
+//                fp32 red.add epilogue straight into the gradient arena.
+#pragma once
+#include "umma_core.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue kinds for GemmPolicy
+enum GemmEpi : int {
+  EPI_F32_STORE = 0,      // out[row*ldo + col] = acc                      (fp32)
+  EPI_F32_ATOMIC = 1,     // out[row*ldo + col] += acc                     (fp32, split-K)
+  EPI_F32_ATOMIC_T = 2,   // out[col*ldo + row] += acc                     (swap-AB FC, split-K)
+  EPI_BF16_BIAS_RELU = 3, // out[row*ldo + col] = bf16(relu(acc + bias[col]))
+  EPI_F32_STORE_T = 4,    // out[col*ldo + row] = acc
+};
+
+struct GemmParams {
+  CUtensorMap mapA;
+  CUtensorMap mapB;
+  int M, N;               // valid output extent (rows of A-side, rows of B-side)
+  int k_iters_total;      // ceil(K / 64)
+  int k_iters_per_split;
+  void* out;
+  long long ldo;
+  const float* bias;
+  float alpha;
+};
+
+template <int BN_, int STAGES_, bool A_MN_, bool B_MN_, int EPI>
+struct GemmPolicy {
+  static constexpr int BN = BN_;
+  static constexpr int STAGES = STAGES_;
+  static constexpr bool A_MN = A_MN_;
+  static constexpr bool B_MN = B_MN_;
+  using Params = GemmParams;
+  struct Ctx {
+    int m0, n0, k_begin, nk;
+  };
+
+  __device__ static void prefetch(const Params& p) {
+    tma_prefetch_desc(&p.mapA);
+    tma_prefetch_desc(&p.mapB);
+  }
+  __device__ static Ctx make_ctx(const Params& p) {
+    Ctx c;
+    c.m0 = blockIdx.x * UMMA_BM;
+    c.n0 = blockIdx.y * BN;
+    c.k_begin = blockIdx.z * p.k_iters_per_split;
+    int rem = p.k_iters_total - c.k_begin;
+    c.nk = rem < 0 ? 0 : (rem < p.k_iters_per_split ? rem : p.k_iters_per_split);
+    return c;
+  }
+  __device__ static int num_k_iters(const Params&, const Ctx& c) { return c.nk; }
+
+  __device__ static void load(const Params& p, const Ctx& c, int i, uint8_t* sA, uint8_t* sB,
+                              uint64_t* bar) {
+    const int k0 = (c.k_begin + i) * UMMA_BK;
+    if constexpr (A_MN) {
+#pragma unroll
+      for (int j = 0; j < UMMA_BM / 64; ++j)
+        tma_load_2d(sA + j * UMMA_SLAB_BYTES, &p.mapA, bar, c.m0 + 64 * j, k0);
+    } else {
+      tma_load_2d(sA, &p.mapA, bar, k0, c.m0);
+    }
+    if constexpr (B_MN) {
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j)
+        tma_load_2d(sB + j * UMMA_SLAB_BYTES, &p.mapB, bar, c.n0 + 64 * j, k0);
+    } else {
+      tma_load_2d(sB, &p.mapB, bar, k0, c.n0);
+    }
+  }
+
+  __device__ static void epilogue(const Params& p, const Ctx& c, int row, int col0,
+                                  const uint32_t (&acc)[32]) {
+    const int r = c.m0 + row;
+    const int cb = c.n0 + col0;
+    if (r >= p.M || cb >= p.N) return;
+    const float alpha = p.alpha;
+    if constexpr (EPI == EPI_F32_STORE || EPI == EPI_F32_ATOMIC) {
+      float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(r) * p.ldo + cb;
+      const bool vec = (cb + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+      if (vec) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(acc[j]) * alpha, __uint_as_float(acc[j + 1]) * alpha,
+                                 __uint_as_float(acc[j + 2]) * alpha, __uint_as_float(acc[j + 3]) * alpha);
+          if constexpr (EPI == EPI_F32_STORE) {
+            *reinterpret_cast<float4*>(o + j) = v;
+          } else {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(v.x),
+                         "f"(v.y), "f"(v.z), "f"(v.w)
+                         : "memory");
+          }
+        }
+      } else {
+        for (int j = 0; j < 32 && cb + j < p.N; ++j) {
+          if constexpr (EPI == EPI_F32_STORE) o[j] = __uint_as_float(acc[j]) * alpha;
+          else atomicAdd(o + j, __uint_as_float(acc[j]) * alpha);
+        }
+      }
+    } else if constexpr (EPI == EPI_F32_ATOMIC_T || EPI == EPI_F32_STORE_T) {
+      float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(cb) * p.ldo + r;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (cb + j < p.N) {
+          if constexpr (EPI == EPI_F32_ATOMIC_T) atomicAdd(o + static_cast<long long>(j) * p.ldo, __uint_as_float(acc[j]) * alpha);
+          else o[static_cast<long long>(j) * p.ldo] = __uint_as_float(acc[j]) * alpha;
+        }
+      }
+    } else if constexpr (EPI == EPI_BF16_BIAS_RELU) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(r) * p.ldo + cb;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          float b = p.bias ? __ldg(p.bias + cb + j + t) : 0.f;
+          v[t] = fmaxf(__uint_as_float(acc[j + t]) + b, 0.f);
+        }
+        uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                              pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(o + j) = pk;
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+struct ConvTile {
+  int N, H, W;            // activation extent
+  int Wb, Hb, Nb;         // pixel box of one tile (Wb*Hb*Nb = 128 for fprop/dgrad, 64 for wgrad)
+  int tiles_w, tiles_h;   // ceil(W/Wb), ceil(H/Hb)
+};
+
+enum ConvFlags : int {
+  CONV_BIAS = 1,          // add bias[channel]
+  CONV_RELU = 2,          // clamp at 0
+  CONV_MASK = 4,          // zero where mask_src <= 0 (ReLU backward fused into dgrad)
+};
+
+struct ConvParams {
+  CUtensorMap mapA;       // activation, dims {Ca, W, H, N}, box {64, Wb, Hb, Nb}
+  CUtensorMap mapB;       // weights as 2-D [Cout][9*Cin]
+  ConvTile t;
+  int Ca;                 // channels of the A activation (GEMM K per tap)
+  int Cn;                 // channels of the output (GEMM N)
+  int wcols_per_tap;      // Cin of the weight tensor (column block per tap)
+  __nv_bfloat16* out;     // NHWC [N][H][W][Cn]
+  const float* bias;
+  const __nv_bfloat16* mask_src;
+  int flags;
+};
+
+__device__ __forceinline__ void conv_tile_origin(const ConvTile& t, int tile, int& n0, int& h0,
+                                                 int& w0) {
+  const int tw = tile % t.tiles_w;
+  const int rest = tile / t.tiles_w;
+  const int th = rest % t.tiles_h;
+  const int tn = rest / t.tiles_h;
+  w0 = tw * t.Wb;
+  h0 = th * t.Hb;
+  n0 = tn * t.Nb;
+}
+
+template <int BN_, int STAGES_, bool DGRAD>
+struct ConvPolicy {
+  static constexpr int BN = BN_;
+  static constexpr int STAGES = STAGES_;
+  static constexpr bool A_MN = false;
+  static constexpr bool B_MN = DGRAD;
+  using Params = ConvParams;
+  struct Ctx {
+    int n0, h0, w0, c0, cchunks;
+  };
+  __device__ static void prefetch(const Params& p) {
+    tma_prefetch_desc(&p.mapA);
+    tma_prefetch_desc(&p.mapB);
+  }
+  __device__ static Ctx make_ctx(const Params& p) {
+    Ctx c;
+    conv_tile_origin(p.t, blockIdx.x, c.n0, c.h0, c.w0);
+    c.c0 = blockIdx.y * BN;
+    c.cchunks = p.Ca / UMMA_BK;
+    return c;
+  }
+  __device__ static int num_k_iters(const Params&, const Ctx& c) { return 9 * c.cchunks; }
+
+  __device__ static void load(const Params& p, const Ctx& c, int i, uint8_t* sA, uint8_t* sB,
+                              uint64_t* bar) {
+    const int tap = i / c.cchunks;
+    const int ck = (i - tap * c.cchunks) * UMMA_BK;
+    const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+    tma_load_4d(sA, &p.mapA, bar, ck, c.w0 + dw, c.h0 + dh, c.n0);
+    if constexpr (!DGRAD) {
+      tma_load_2d(sB, &p.mapB, bar, tap * p.wcols_per_tap + ck, c.c0);
+    } else {
+      const int wt = 8 - tap;          // mirrored tap: dX[q] = sum dZ[q + (kh'-1, kw'-1)] W[2-kh'][2-kw']
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j)
+        tma_load_2d(sB + j * UMMA_SLAB_BYTES, &p.mapB, bar, wt * p.wcols_per_tap + c.c0 + 64 * j, ck);
+    }
+  }
+
+  __device__ static void epilogue(const Params& p, const Ctx& c, int row, int col0,
+                                  const uint32_t (&acc)[32]) {
+    const ConvTile& t = p.t;
+    const int ww = row % t.Wb;
+    const int r2 = row / t.Wb;
+    const int hh = r2 % t.Hb;
+    const int nn = r2 / t.Hb;
+    const int n = c.n0 + nn, h = c.h0 + hh, w = c.w0 + ww;
+    const int ch = c.c0 + col0;
+    if (n >= t.N || h >= t.H || w >= t.W || ch >= p.Cn) return;
+    const long long off = ((static_cast<long long>(n) * t.H + h) * t.W + w) * p.Cn + ch;
+    __nv_bfloat16* o = p.out + off;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(acc[j + u]);
+      if (p.flags & CONV_BIAS) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch + j));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch + j + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (p.flags & CONV_RELU) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
+      }
+      if (p.flags & CONV_MASK) {
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask_src + off + j));
+        const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 f = unpack_bf16x2(mw[u]);
+          if (!(f.x > 0.f)) v[2 * u] = 0.f;
+          if (!(f.y > 0.f)) v[2 * u + 1] = 0.f;
+        }
+      }
+      const uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                  pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(o + j) = pk;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+struct WgradParams {
+  CUtensorMap mapA;       // dZ, dims {Cout, W, H, N}, box {64, Wb, Hb, Nb} (64 pixels)
+  CUtensorMap mapB;       // X,  dims {Cin,  W, H, N}, same box
+  ConvTile t;
+  int Cout, Cin;
+  int total_tiles;        // pixel tiles = tiles_w * tiles_h * tiles_n
+  int tiles_per_split;
+  int ksplit;
+  float* dW;              // [Cout][9][Cin] fp32, accumulated with red.add
+  float scale;
+};
+
+template <int BN_, int STAGES_>
+struct WgradPolicy {
+  static constexpr int BN = BN_;
+  static constexpr int STAGES = STAGES_;
+  static constexpr bool A_MN = true;
+  static constexpr bool B_MN = true;
+  using Params = WgradParams;
+  struct Ctx {
+    int m0, c0, tap, tile_begin, nk;
+  };
+  __device__ static void prefetch(const Params& p) {
+    tma_prefetch_desc(&p.mapA);
+    tma_prefetch_desc(&p.mapB);
+  }
+  __device__ static Ctx make_ctx(const Params& p) {
+    Ctx c;
+    c.m0 = blockIdx.x * UMMA_BM;
+    c.c0 = blockIdx.y * BN;
+    c.tap = blockIdx.z / p.ksplit;
+    const int split = blockIdx.z - c.tap * p.ksplit;
+    c.tile_begin = split * p.tiles_per_split;
+    int rem = p.total_tiles - c.tile_begin;
+    c.nk = rem < 0 ? 0 : (rem < p.tiles_per_split ? rem : p.tiles_per_split);
+    return c;
+  }
+  __device__ static int num_k_iters(const Params&, const Ctx& c) { return c.nk; }
+
+  __device__ static void load(const Params& p, const Ctx& c, int i, uint8_t* sA, uint8_t* sB,
+                              uint64_t* bar) {
+    int n0, h0, w0;
+    conv_tile_origin(p.t, c.tile_begin + i, n0, h0, w0);
+    const int dh = c.tap / 3 - 1, dw = c.tap % 3 - 1;
+#pragma unroll
+    for (int j = 0; j < UMMA_BM / 64; ++j)
+      tma_load_4d(sA + j * UMMA_SLAB_BYTES, &p.mapA, bar, c.m0 + 64 * j, w0, h0, n0);
+#pragma unroll
+    for (int j = 0; j < BN / 64; ++j)
+      tma_load_4d(sB + j * UMMA_SLAB_BYTES, &p.mapB, bar, c.c0 + 64 * j, w0 + dw, h0 + dh, n0);
+  }
+
+  __device__ static void epilogue(const Params& p, const Ctx& c, int row, int col0,
+                                  const uint32_t (&acc)[32]) {
+    const int co = c.m0 + row;
+    const int ci = c.c0 + col0;
+    if (co >= p.Cout || ci >= p.Cin) return;
+    float* o = p.dW + (static_cast<long long>(co) * 9 + c.tap) * p.Cin + ci;
+    const float s = p.scale;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j),
+                   "f"(__uint_as_float(acc[j]) * s), "f"(__uint_as_float(acc[j + 1]) * s),
+                   "f"(__uint_as_float(acc[j + 2]) * s), "f"(__uint_as_float(acc[j + 3]) * s)
+                   : "memory");
+    }
+  }
+};
+
+}  // namespace b200

@@ -1,0 +1,199 @@
+// Fused cross-entropy (forward + backward + metrics) and the fused flat-arena optimizers.
+//
+// Reference semantics: F.cross_entropy(outputs, targets) with mean reduction
+// (distributedVggf.py:168), Accuracy2 = argmax == target count (distributedUtil.py:92-99),
+// Average = sample-weighted loss mean (distributedUtil.py:55-58), torch.optim.Adam with default
+// betas/eps (distributedVggf.py:230).  The reference pays two host syncs per step for the metrics;
+// here they are three atomics into a device meter.
+#include <stdexcept>
+
+#include "api.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+// One block, one warp per row (round-robin).  C is small (3) or moderate (1000).
+__global__ void cross_entropy_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                     bf16* __restrict__ dlogits, int ldd, float* __restrict__ meter,
+                                     float* __restrict__ loss_out, int B, int C, float grad_scale,
+                                     const float* __restrict__ cw) {
+  __shared__ float s_loss[32], s_correct[32], s_wsum[32];
+  __shared__ float s_total_w;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+
+  // pass 0 (only with class weights): normaliser = sum_i w[target_i]
+  float wsum_local = 0.f;
+  if (cw) {
+    for (int r = threadIdx.x; r < B; r += blockDim.x) wsum_local += cw[target[r]];
+    for (int o = 16; o; o >>= 1) wsum_local += __shfl_xor_sync(0xffffffffu, wsum_local, o);
+    if (lane == 0) s_wsum[warp] = wsum_local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < nwarps; ++i) t += s_wsum[i];
+      s_total_w = t;
+    }
+    __syncthreads();
+  }
+  const float norm = cw ? 1.f / s_total_w : grad_scale;   // grad_scale == 1/B for the mean
+
+  float loss_acc = 0.f, correct_acc = 0.f;
+  for (int r = warp; r < B; r += nwarps) {
+    const float* row = logits + static_cast<long long>(r) * C;
+    const int t = static_cast<int>(target[r]);
+    float mx = -INFINITY;
+    int amax = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+      const float v = row[c];
+      if (v > mx) { mx = v; amax = c; }
+    }
+    for (int o = 16; o; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, amax, o);
+      if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
+    }
+    float se = 0.f;
+    for (int c = lane; c < C; c += 32) se += __expf(row[c] - mx);
+    for (int o = 16; o; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    const float lse = mx + __logf(se);
+    const float w = cw ? cw[t] : 1.f;
+    if (dlogits) {
+      for (int c = lane; c < ldd; c += 32) {
+        float g = 0.f;
+        if (c < C) g = (__expf(row[c] - lse) - (c == t ? 1.f : 0.f)) * w * norm;
+        dlogits[static_cast<long long>(r) * ldd + c] = __float2bfloat16(g);
+      }
+    }
+    if (lane == 0) {
+      loss_acc += lse - row[t];
+      correct_acc += (amax == t) ? 1.f : 0.f;
+    }
+  }
+  if (lane == 0) { s_loss[warp] = loss_acc; s_correct[warp] = correct_acc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tl = 0.f, tc = 0.f;
+    for (int i = 0; i < nwarps; ++i) { tl += s_loss[i]; tc += s_correct[i]; }
+    if (meter) {
+      atomicAdd(meter + 0, tl);
+      atomicAdd(meter + 1, tc);
+      atomicAdd(meter + 2, static_cast<float>(B));
+    }
+    if (loss_out) *loss_out = tl / static_cast<float>(B);
+  }
+}
+
+void cross_entropy_fused(const float* logits, const long long* target, bf16* dlogits, int ldd,
+                         float* meter, float* loss_out, int B, int C, float grad_scale,
+                         const float* class_weights, cudaStream_t s) {
+  cross_entropy_kernel<<<1, 1024, 0, s>>>(logits, target, dlogits, ldd, meter, loss_out, B, C,
+                                          grad_scale, class_weights);
+  count_launch();
+  check_last("cross_entropy_fused");
+}
+
+// ---------------------------------------------------------------------------------------- Adam
+// One pass over the flat arena: read grad (fp32 local or bf16 reduced wire), update fp32 master
+// weight and both moments, emit the bf16 shadow used by the GEMMs, and zero the fp32 gradient so
+// the red.add wgrad epilogues of the next step start from zero.
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                            const float* __restrict__ g32, const bf16* __restrict__ g16,
+                            bf16* __restrict__ shadow, long long n4, float lr, float b1, float b2,
+                            float eps, float wd, float bc1_inv, float bc2_inv_sqrt, float gscale,
+                            float* __restrict__ gzero) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float g[4];
+    if (g16) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(g16 + i * 4);
+      const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
+      g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
+    } else {
+      const float4 gv = reinterpret_cast<const float4*>(g32)[i];
+      g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+    }
+    float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+    float mm[4] = {mv.x, mv.y, mv.z, mv.w};
+    float vs[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gk = g[k] * gscale + wd * pp[k];
+      mm[k] = b1 * mm[k] + (1.f - b1) * gk;
+      vs[k] = b2 * vs[k] + (1.f - b2) * gk * gk;
+      const float denom = sqrtf(vs[k]) * bc2_inv_sqrt + eps;
+      pp[k] -= lr * bc1_inv * mm[k] / denom;
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(vs[0], vs[1], vs[2], vs[3]);
+    if (shadow)
+      *reinterpret_cast<uint2*>(shadow + i * 4) = make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
+    if (gzero) reinterpret_cast<float4*>(gzero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+void adam_fused(float* p, float* m, float* v, const float* g32, const bf16* g16, bf16* shadow,
+                long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                int step, float grad_scale, bool, float* g32_to_zero, cudaStream_t s) {
+  if (n % 4) throw std::runtime_error("[b200] adam_fused: n must be a multiple of 4");
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  const long long n4 = n / 4;
+  const int blocks = static_cast<int>(n4 / 256 + 1 < 148 * 8 ? n4 / 256 + 1 : 148 * 8);
+  adam_kernel<<<blocks, 256, 0, s>>>(p, m, v, g32, g16, shadow, n4, lr, beta1, beta2, eps, weight_decay,
+                                     static_cast<float>(1.0 / bc1), static_cast<float>(1.0 / sqrt(bc2)),
+                                     grad_scale, g32_to_zero);
+  count_launch();
+  check_last("adam_fused");
+}
+
+// --------------------------------------------------------------------------------------- SGD
+// torch.optim.SGD(momentum) semantics: buf = g (first step) | momentum*buf + g ; p -= lr*buf.
+__global__ void sgd_kernel(float* __restrict__ p, float* __restrict__ mom, const float* __restrict__ g32,
+                           const bf16* __restrict__ g16, bf16* __restrict__ shadow, long long n4, float lr,
+                           float momentum, float wd, int first, float gscale, float* __restrict__ gzero) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float4 bv = reinterpret_cast<float4*>(mom)[i];
+    float g[4];
+    if (g16) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(g16 + i * 4);
+      const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
+      g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
+    } else {
+      const float4 gv = reinterpret_cast<const float4*>(g32)[i];
+      g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+    }
+    float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+    float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = g[k] * gscale + wd * pp[k];
+      bb[k] = first ? gk : momentum * bb[k] + gk;
+      pp[k] -= lr * bb[k];
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(mom)[i] = make_float4(bb[0], bb[1], bb[2], bb[3]);
+    if (shadow)
+      *reinterpret_cast<uint2*>(shadow + i * 4) = make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
+    if (gzero) reinterpret_cast<float4*>(gzero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+void sgd_fused(float* p, float* mom, const float* g32, const bf16* g16, bf16* shadow, long long n,
+               float lr, float momentum, float weight_decay, bool first_step, float grad_scale,
+               float* g32_to_zero, cudaStream_t s) {
+  if (n % 4) throw std::runtime_error("[b200] sgd_fused: n must be a multiple of 4");
+  const long long n4 = n / 4;
+  const int blocks = static_cast<int>(n4 / 256 + 1 < 148 * 8 ? n4 / 256 + 1 : 148 * 8);
+  sgd_kernel<<<blocks, 256, 0, s>>>(p, mom, g32, g16, shadow, n4, lr, momentum, weight_decay,
+                                    first_step ? 1 : 0, grad_scale, g32_to_zero);
+  count_launch();
+  check_last("sgd_fused");
+}
+
+}  // namespace b200

@@ -1,0 +1,258 @@
+// Host side of the tcgen05 GEMM / convolution family: builds the TMA tensor maps
+// (cuTensorMapEncodeTiled through the runtime's driver entry point, so nothing links libcuda),
+// picks the tile width and launches umma_kernel<Policy>.
+#include <cudaTypedefs.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+#include "api.h"
+#include "umma_policies.cuh"
+
+namespace b200 {
+
+static std::atomic<long long> g_launches{0};
+long long launch_count() { return g_launches.load(); }
+void count_launch(int n) { g_launches.fetch_add(n); }
+void check_last(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    throw std::runtime_error(std::string("[b200] ") + what + ": " + cudaGetErrorString(e));
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+      throw std::runtime_error("[b200] cuTensorMapEncodeTiled entry point not available");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+static void encode(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims,
+                   const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0)
+    throw std::runtime_error("[b200] TMA base pointer must be 16-byte aligned");
+  for (int i = 0; i < rank - 1; ++i)
+    if (strides_bytes[i] % 16 != 0)
+      throw std::runtime_error("[b200] TMA strides must be multiples of 16 bytes");
+  CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr),
+                           dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "[b200] cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu box %u %u", (int)r,
+             rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    throw std::runtime_error(buf);
+  }
+}
+
+// 2-D row-major matrix [rows][cols] (row stride ld elements); box = {box_cols, box_rows}.
+static void map_2d(CUtensorMap* m, const bf16* p, long long rows, long long cols, long long ld,
+                   int box_cols, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t str[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  encode(m, p, 2, dims, str, box);
+}
+// NHWC activation as {C, W, H, N}; box = {64, Wb, Hb, Nb}.
+static void map_nhwc(CUtensorMap* m, const bf16* p, int N, int H, int W, int C, int Wb, int Hb,
+                     int Nb) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t str[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)Wb, (cuuint32_t)Hb, (cuuint32_t)Nb};
+  encode(m, p, 4, dims, str, box);
+}
+
+template <class P>
+static void launch(const typename P::Params& prm, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = umma_smem_bytes<P::BN, P::STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(umma_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess)
+      throw std::runtime_error(std::string("[b200] cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  umma_kernel<P><<<grid, UMMA_THREADS, smem, stream>>>(prm);
+  count_launch();
+  check_last("umma_kernel launch");
+}
+
+static int largest_pow2_divisor(int x, int cap) {
+  int p = 1;
+  while (p * 2 <= cap && x % (p * 2) == 0) p *= 2;
+  return p;
+}
+// Pixel box {Wb, Hb, Nb} with Wb*Hb*Nb == pixels, following the power-of-two factors of W and H
+// (224 = 7*32 -> 32x4x1, 112 -> 16x8x1, 56 -> 8x8x2, 28 -> 4x4x8, 14 -> 2x2x32).
+static ConvTile make_tile(int N, int H, int W, int pixels) {
+  ConvTile t;
+  t.N = N; t.H = H; t.W = W;
+  t.Wb = largest_pow2_divisor(W, pixels < 32 ? pixels : 32);
+  t.Hb = largest_pow2_divisor(H, pixels / t.Wb);
+  t.Nb = pixels / (t.Wb * t.Hb);
+  t.tiles_w = (W + t.Wb - 1) / t.Wb;
+  t.tiles_h = (H + t.Hb - 1) / t.Hb;
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------- GEMM
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static void gemm_launch(GemmParams& prm, const bf16* A, long long lda, const bf16* B, long long ldb,
+                        int M, int N, int K, int ksplit, cudaStream_t stream) {
+  constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  using P = GemmPolicy<BN, STAGES, A_MN, B_MN, EPI>;
+  if (A_MN) map_2d(&prm.mapA, A, K, M, lda, 64, 64); else map_2d(&prm.mapA, A, M, K, lda, 64, UMMA_BM);
+  if (B_MN) map_2d(&prm.mapB, B, K, N, ldb, 64, 64); else map_2d(&prm.mapB, B, N, K, ldb, 64, BN);
+  dim3 grid((M + UMMA_BM - 1) / UMMA_BM, (N + BN - 1) / BN, ksplit);
+  launch<P>(prm, grid, stream);
+}
+
+#define GEMM_BN_SWITCH(AMN, BMN, EPI)                                                       \
+  switch (bn) {                                                                             \
+    case 64:  gemm_launch<64,  AMN, BMN, EPI>(prm, A, lda, B, ldb, M, N, K, ksplit, stream); return; \
+    case 128: gemm_launch<128, AMN, BMN, EPI>(prm, A, lda, B, ldb, M, N, K, ksplit, stream); return; \
+    case 256: gemm_launch<256, AMN, BMN, EPI>(prm, A, lda, B, ldb, M, N, K, ksplit, stream); return; \
+    default: break;                                                                         \
+  }
+#define GEMM_BN_SWITCH_32(AMN, BMN, EPI)                                                    \
+  if (bn == 32) { gemm_launch<32, AMN, BMN, EPI>(prm, A, lda, B, ldb, M, N, K, ksplit, stream); return; } \
+  GEMM_BN_SWITCH(AMN, BMN, EPI)
+
+void gemm_bf16(const bf16* A, long long lda, bool a_mn, const bf16* B, long long ldb, bool b_mn,
+               int M, int N, int K, void* out, long long ldo, int epi, const float* bias,
+               float alpha, int ksplit, int bn, cudaStream_t stream) {
+  if (bn == 0) bn = N <= 32 && !b_mn ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  if (ksplit < 1) ksplit = 1;
+  GemmParams prm;
+  prm.M = M; prm.N = N;
+  prm.k_iters_total = (K + UMMA_BK - 1) / UMMA_BK;
+  prm.k_iters_per_split = (prm.k_iters_total + ksplit - 1) / ksplit;
+  ksplit = (prm.k_iters_total + prm.k_iters_per_split - 1) / prm.k_iters_per_split;
+  prm.out = out; prm.ldo = ldo; prm.bias = bias; prm.alpha = alpha;
+  if (ksplit > 1 && !(epi == EPI_F32_ATOMIC || epi == EPI_F32_ATOMIC_T))
+    throw std::runtime_error("[b200] gemm_bf16: split-K needs an atomic epilogue");
+  if (!a_mn && !b_mn) {
+    if (epi == EPI_F32_ATOMIC_T) { GEMM_BN_SWITCH_32(false, false, EPI_F32_ATOMIC_T) }
+    if (epi == EPI_F32_STORE_T) { GEMM_BN_SWITCH_32(false, false, EPI_F32_STORE_T) }
+    if (epi == EPI_BF16_BIAS_RELU) { GEMM_BN_SWITCH(false, false, EPI_BF16_BIAS_RELU) }
+    if (epi == EPI_F32_STORE) { GEMM_BN_SWITCH(false, false, EPI_F32_STORE) }
+  } else if (a_mn && !b_mn) {
+    if (epi == EPI_F32_ATOMIC_T) { GEMM_BN_SWITCH_32(true, false, EPI_F32_ATOMIC_T) }
+    if (epi == EPI_F32_STORE_T) { GEMM_BN_SWITCH_32(true, false, EPI_F32_STORE_T) }
+  } else if (a_mn && b_mn) {
+    if (epi == EPI_F32_STORE) { GEMM_BN_SWITCH(true, true, EPI_F32_STORE) }
+    if (epi == EPI_F32_ATOMIC) { GEMM_BN_SWITCH(true, true, EPI_F32_ATOMIC) }
+  }
+  throw std::runtime_error("[b200] gemm_bf16: unsupported (layout, epilogue, bn) combination");
+}
+
+// ---------------------------------------------------------------------------------------- conv
+static void check_channels(int c, const char* what) {
+  if (c % 64 != 0) throw std::runtime_error(std::string("[b200] ") + what + " must be a multiple of 64");
+}
+
+template <int BN, bool DGRAD>
+static void conv_launch(ConvParams& prm, cudaStream_t stream) {
+  constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  using P = ConvPolicy<BN, STAGES, DGRAD>;
+  const ConvTile& t = prm.t;
+  const int tiles_n = (t.N + t.Nb - 1) / t.Nb;
+  dim3 grid(t.tiles_w * t.tiles_h * tiles_n, (prm.Cn + BN - 1) / BN, 1);
+  launch<P>(prm, grid, stream);
+}
+
+static int auto_bn(int cn, int bn) {
+  if (bn) return bn;
+  return cn <= 64 ? 64 : (cn <= 128 ? 128 : 256);
+}
+
+void conv3x3_fprop(const bf16* x, const bf16* w, const float* bias, bf16* y, int N, int H, int W,
+                   int Cin, int Cout, bool relu, int bn, cudaStream_t stream) {
+  check_channels(Cin, "conv3x3_fprop Cin");
+  check_channels(Cout, "conv3x3_fprop Cout");
+  ConvParams prm;
+  prm.t = make_tile(N, H, W, UMMA_BM);
+  prm.Ca = Cin; prm.Cn = Cout; prm.wcols_per_tap = Cin;
+  prm.out = y; prm.bias = bias; prm.mask_src = nullptr;
+  prm.flags = (bias ? CONV_BIAS : 0) | (relu ? CONV_RELU : 0);
+  bn = auto_bn(Cout, bn);
+  map_nhwc(&prm.mapA, x, N, H, W, Cin, prm.t.Wb, prm.t.Hb, prm.t.Nb);
+  map_2d(&prm.mapB, w, Cout, 9LL * Cin, 9LL * Cin, 64, bn);
+  switch (bn) {
+    case 64: conv_launch<64, false>(prm, stream); break;
+    case 128: conv_launch<128, false>(prm, stream); break;
+    case 256: conv_launch<256, false>(prm, stream); break;
+    default: throw std::runtime_error("[b200] conv3x3_fprop: bn must be 64/128/256");
+  }
+}
+
+void conv3x3_dgrad(const bf16* dz, const bf16* w, const bf16* mask_src, bf16* dx, int N, int H,
+                   int W, int Cin, int Cout, int bn, cudaStream_t stream) {
+  check_channels(Cin, "conv3x3_dgrad Cin");
+  check_channels(Cout, "conv3x3_dgrad Cout");
+  ConvParams prm;
+  prm.t = make_tile(N, H, W, UMMA_BM);
+  prm.Ca = Cout; prm.Cn = Cin; prm.wcols_per_tap = Cin;
+  prm.out = dx; prm.bias = nullptr; prm.mask_src = mask_src;
+  prm.flags = mask_src ? CONV_MASK : 0;
+  bn = auto_bn(Cin, bn);
+  map_nhwc(&prm.mapA, dz, N, H, W, Cout, prm.t.Wb, prm.t.Hb, prm.t.Nb);
+  map_2d(&prm.mapB, w, Cout, 9LL * Cin, 9LL * Cin, 64, 64);   // MN-major: 64 ci x 64 co boxes
+  switch (bn) {
+    case 64: conv_launch<64, true>(prm, stream); break;
+    case 128: conv_launch<128, true>(prm, stream); break;
+    case 256: conv_launch<256, true>(prm, stream); break;
+    default: throw std::runtime_error("[b200] conv3x3_dgrad: bn must be 64/128/256");
+  }
+}
+
+template <int BN>
+static void wgrad_launch(WgradParams& prm, cudaStream_t stream) {
+  constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  using P = WgradPolicy<BN, STAGES>;
+  dim3 grid((prm.Cout + UMMA_BM - 1) / UMMA_BM, (prm.Cin + BN - 1) / BN, 9 * prm.ksplit);
+  launch<P>(prm, grid, stream);
+}
+
+void conv3x3_wgrad(const bf16* dz, const bf16* x, float* dw, int N, int H, int W, int Cin,
+                   int Cout, float scale, int ksplit, int bn, cudaStream_t stream) {
+  check_channels(Cin, "conv3x3_wgrad Cin");
+  check_channels(Cout, "conv3x3_wgrad Cout");
+  WgradParams prm;
+  prm.t = make_tile(N, H, W, 64);
+  const int tiles_n = (N + prm.t.Nb - 1) / prm.t.Nb;
+  prm.Cout = Cout; prm.Cin = Cin;
+  prm.total_tiles = prm.t.tiles_w * prm.t.tiles_h * tiles_n;
+  bn = auto_bn(Cin, bn);
+  if (ksplit <= 0) {     // fill ~2 waves of 148 SMs
+    const int base = ((Cout + UMMA_BM - 1) / UMMA_BM) * ((Cin + bn - 1) / bn) * 9;
+    ksplit = (2 * 148 + base - 1) / base;
+    if (ksplit < 1) ksplit = 1;
+  }
+  if (ksplit > prm.total_tiles) ksplit = prm.total_tiles;
+  prm.tiles_per_split = (prm.total_tiles + ksplit - 1) / ksplit;
+  prm.ksplit = (prm.total_tiles + prm.tiles_per_split - 1) / prm.tiles_per_split;
+  prm.dW = dw; prm.scale = scale;
+  map_nhwc(&prm.mapA, dz, N, H, W, Cout, prm.t.Wb, prm.t.Hb, prm.t.Nb);
+  map_nhwc(&prm.mapB, x, N, H, W, Cin, prm.t.Wb, prm.t.Hb, prm.t.Nb);
+  switch (bn) {
+    case 64: wgrad_launch<64>(prm, stream); break;
+    case 128: wgrad_launch<128>(prm, stream); break;
+    case 256: wgrad_launch<256>(prm, stream); break;
+    default: throw std::runtime_error("[b200] conv3x3_wgrad: bn must be 64/128/256");
+  }
+}
+
+}  // namespace b200

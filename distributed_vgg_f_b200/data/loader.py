@@ -1,0 +1,216 @@
+"""DataManager: ImageFolder -> mini-batches, in two flavours.
+
+Reference (distributedVggf.py:63-123): ``DataManager(root_folder, mini_batch, train)`` exposes
+``class_names / number_classes / data_size / loader / get_loader()``; the loader is a synchronous
+``DataLoader(num_workers=0, pin_memory=False)`` over PIL transforms, sharded by a
+``DistributedSampler`` only for the training split (validation runs in full on every rank).
+
+Same surface here, two pipelines:
+  * ``pipeline="reference"`` -- PIL decode + the literal torchvision transforms per sample.  Yields
+    ``(float32 [mb,3,224,224], int64 [mb])``.  Bit-level semantics of the reference; ~400 img/s.
+  * ``pipeline="fused"`` (default) -- every image is decoded ONCE into a uint8 cache (thread pool),
+    a background thread gathers each batch into a pinned staging ring together with the sampled
+    transform parameters, and the consumer runs the fused augment op on the device.  Yields
+    ``FusedBatch``.  Requires a uniform source size (true for COIL-100 / the synthetic set).
+Ragged final batches are preserved (``drop_last=False`` in the reference).
+"""
+from __future__ import annotations
+
+import os
+import queue
+import threading
+from concurrent.futures import ThreadPoolExecutor
+from typing import Iterator, List, NamedTuple, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ..config import DATA
+from . import transforms as T
+from .folder import scan_image_folder
+from .sampler import ShardedSampler
+
+
+class FusedBatch(NamedTuple):
+    images_u8: torch.Tensor     # uint8 [mb, H, W, 3] (pinned when CUDA is present)
+    params: torch.Tensor        # float32 [mb, 8]     (same)
+    labels: torch.Tensor        # int64 [mb]          (same)
+    resized_hw: Tuple[int, int]
+
+    def to_float(self, device="cpu") -> Tuple[torch.Tensor, torch.Tensor]:
+        """Evaluate the fused transform with torch ops (CPU / oracle path)."""
+        x = T.augment_reference(self.images_u8.to(device), self.params, self.resized_hw)
+        return x, self.labels.to(device)
+
+
+def _decode(path: str) -> np.ndarray:
+    from PIL import Image
+
+    with open(path, "rb") as f:
+        return np.asarray(Image.open(f).convert("RGB"), dtype=np.uint8)
+
+
+class DecodedCache:
+    """All images of a split, decoded once to uint8 HWC (optionally by the native PNG decoder)."""
+
+    def __init__(self, samples: List[Tuple[str, int]], threads: int = 8) -> None:
+        paths = [p for p, _ in samples]
+        arrays = None
+        try:   # native multi-threaded PNG decode (csrc/png_decode.cpp), falls back to PIL
+            from ..ops import native_decode_pngs
+            arrays = native_decode_pngs(paths, threads)
+        except Exception:
+            arrays = None
+        if arrays is None:
+            with ThreadPoolExecutor(max_workers=threads) as ex:
+                arrays = list(ex.map(_decode, paths))
+        shapes = {a.shape for a in arrays}
+        if len(shapes) != 1:
+            raise ValueError("fused pipeline needs a uniform image size, found %s; "
+                             "use pipeline='reference'" % sorted(shapes)[:4])
+        self.images = torch.from_numpy(np.stack(arrays))              # [N,H,W,3] uint8
+        self.labels = torch.tensor([l for _, l in samples], dtype=torch.int64)
+        self.src_hw = (int(self.images.shape[1]), int(self.images.shape[2]))
+
+
+class _FusedLoader:
+    def __init__(self, cache: DecodedCache, mb: int, train: bool, sampler: Optional[ShardedSampler],
+                 shuffle: bool, seed: int, prefetch: int = 2, pin: Optional[bool] = None) -> None:
+        self.cache, self.mb, self.train = cache, mb, train
+        self.sampler, self.shuffle, self.seed = sampler, shuffle, seed
+        self.prefetch = prefetch
+        self.pin = torch.cuda.is_available() if pin is None else pin
+        self.epoch = 0
+        H, W = cache.src_hw
+        self.resized_hw = T.resized_dims(train, H, W)
+        self._ring = []
+        for _ in range(prefetch + 1):
+            self._ring.append((self._buf((mb, H, W, 3), torch.uint8),
+                               self._buf((mb, T.PARAM_DIM), torch.float32),
+                               self._buf((mb,), torch.int64)))
+
+    def _buf(self, shape, dtype):
+        t = torch.empty(shape, dtype=dtype)
+        return t.pin_memory() if self.pin else t
+
+    def __len__(self) -> int:
+        n = len(self.sampler) if self.sampler is not None else len(self.cache.labels)
+        return (n + self.mb - 1) // self.mb
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = epoch
+        if self.sampler is not None:
+            self.sampler.set_epoch(epoch)
+
+    def _indices(self) -> List[int]:
+        if self.sampler is not None:
+            return list(iter(self.sampler))
+        n = len(self.cache.labels)
+        if self.shuffle:
+            g = torch.Generator().manual_seed(self.seed + self.epoch)
+            return torch.randperm(n, generator=g).tolist()
+        return list(range(n))
+
+    def __iter__(self) -> Iterator[FusedBatch]:
+        idx = self._indices()
+        gen = torch.Generator().manual_seed(1_000_003 * (self.seed + 1) + self.epoch * 7919 +
+                                            (self.sampler.rank if self.sampler else 0))
+        H, W = self.cache.src_hw
+        q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)
+        free: "queue.Queue" = queue.Queue()
+        for slot in range(len(self._ring)):
+            free.put(slot)
+
+        def produce():
+            for b0 in range(0, len(idx), self.mb):
+                sel = torch.tensor(idx[b0:b0 + self.mb], dtype=torch.int64)
+                k = len(sel)
+                slot = free.get()
+                img, par, lab = self._ring[slot]
+                torch.index_select(self.cache.images, 0, sel, out=img[:k])
+                torch.index_select(self.cache.labels, 0, sel, out=lab[:k])
+                par[:k] = (T.sample_train_params(k, H, W, gen) if self.train
+                           else T.val_params(k, H, W))
+                q.put((slot, k))
+            q.put(None)
+
+        th = threading.Thread(target=produce, daemon=True)
+        th.start()
+        prev = None
+        while True:
+            item = q.get()
+            if prev is not None:
+                free.put(prev)      # consumer is done with the previous slot once it asks for more
+            if item is None:
+                break
+            slot, k = item
+            img, par, lab = self._ring[slot]
+            prev = slot
+            yield FusedBatch(img[:k], par[:k], lab[:k], self.resized_hw)
+        th.join()
+
+
+class _ReferenceLoader:
+    """Synchronous PIL + torchvision loader with the reference's exact semantics."""
+
+    def __init__(self, samples, mb: int, train: bool, sampler: Optional[ShardedSampler],
+                 shuffle: bool, seed: int) -> None:
+        self.samples, self.mb, self.sampler = samples, mb, sampler
+        self.shuffle, self.seed, self.epoch = shuffle, seed, 0
+        self.tf = T.reference_transforms(train)
+
+    def __len__(self) -> int:
+        n = len(self.sampler) if self.sampler is not None else len(self.samples)
+        return (n + self.mb - 1) // self.mb
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = epoch
+        if self.sampler is not None:
+            self.sampler.set_epoch(epoch)
+
+    def __iter__(self):
+        from PIL import Image
+
+        if self.sampler is not None:
+            idx = list(iter(self.sampler))
+        elif self.shuffle:
+            idx = torch.randperm(len(self.samples)).tolist()
+        else:
+            idx = list(range(len(self.samples)))
+        for b0 in range(0, len(idx), self.mb):
+            xs, ys = [], []
+            for i in idx[b0:b0 + self.mb]:
+                path, label = self.samples[i]
+                with open(path, "rb") as f:
+                    xs.append(self.tf(Image.open(f).convert("RGB")))
+                ys.append(label)
+            yield torch.stack(xs), torch.tensor(ys, dtype=torch.int64)
+
+
+class DataManager:
+    """Same constructor / attributes as the reference's class (distributedVggf.py:63-123)."""
+
+    def __init__(self, root_folder: str, mini_batch: int, train: bool = True, *,
+                 world_size: int = 1, rank: int = 0, pipeline: str = "fused", seed: int = 0,
+                 reference_order: bool = False, decode_threads: int = 8) -> None:
+        if root_folder is None:
+            raise ValueError("-rd/--root_dir is required")
+        self.root_folder, self.mb_size, self.train = root_folder, mini_batch, train
+        self.path = os.path.join(root_folder, DATA.train_dir if train else DATA.val_dir)
+        self.class_names, self.samples = scan_image_folder(self.path)
+        self.number_classes = len(self.class_names)
+        self.data_size = len(self.samples)
+        sampler = None
+        if train and world_size > 1:      # validation is NOT sharded (distributedVggf.py:115)
+            sampler = ShardedSampler(self.data_size, world_size, rank, seed=seed,
+                                     reference_order=reference_order)
+        if pipeline == "fused":
+            self.cache = DecodedCache(self.samples, decode_threads)
+            self.loader = _FusedLoader(self.cache, mini_batch, train, sampler, True, seed)
+        elif pipeline == "reference":
+            self.loader = _ReferenceLoader(self.samples, mini_batch, train, sampler, True, seed)
+        else:
+            raise ValueError("pipeline must be 'fused' or 'reference'")
+
+    def get_loader(self):
+        return self.loader

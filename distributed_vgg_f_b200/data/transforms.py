@@ -1,0 +1,149 @@
+"""Input transforms as *parameters + one fused sampling op*.
+
+Reference pipelines (distributedVggf.py:88-95 train, :103-108 val), all on PIL images in the
+training process:
+  train: RandomResizedCrop(256, scale=(.8,1)) -> RandomRotation(10) -> RandomHorizontalFlip ->
+         CenterCrop(224) -> ToTensor -> Normalize(ImageNet mean/std)
+  val:   Resize(256) -> CenterCrop(224) -> ToTensor -> Normalize
+Every stage is a coordinate map, so the whole chain collapses into "for each of the 224x224 output
+pixels: undo centre-crop, undo flip, undo rotation (nearest, zero fill), bilinear-sample the crop
+box of the source".  We draw the random parameters on the host with torchvision's exact
+distributions (``sample_train_params``) and evaluate the chain in one pass:
+``augment_reference`` (torch ops; CPU path and oracle) and ``ops.augment`` (sm_100a kernel that
+reads uint8 HWC and writes normalised bf16 NHWC / the layer-0 im2col matrix directly).
+``reference_transforms`` returns the literal torchvision pipeline for bit-level parity runs.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from ..config import DATA
+
+# params row: [top, left, crop_h, crop_w, cos(theta), sin(theta), flip, _]
+PARAM_DIM = 8
+
+
+def sample_train_params(n: int, src_h: int, src_w: int,
+                        generator: Optional[torch.Generator] = None,
+                        scale=DATA.crop_scale, ratio=DATA.crop_ratio,
+                        degrees: float = DATA.rotation_deg) -> torch.Tensor:
+    """Random crop box / angle / flip per sample, distributed as torchvision's get_params."""
+    out = torch.zeros(n, PARAM_DIM, dtype=torch.float32)
+    area = float(src_h * src_w)
+    log_lo, log_hi = math.log(ratio[0]), math.log(ratio[1])
+    u = torch.rand(n, 10, 2, generator=generator)
+    pos = torch.rand(n, 2, generator=generator)
+    misc = torch.rand(n, 2, generator=generator)
+    for s in range(n):
+        box = None
+        for t in range(10):
+            target_area = area * (scale[0] + (scale[1] - scale[0]) * float(u[s, t, 0]))
+            aspect = math.exp(log_lo + (log_hi - log_lo) * float(u[s, t, 1]))
+            w = int(round(math.sqrt(target_area * aspect)))
+            h = int(round(math.sqrt(target_area / aspect)))
+            if 0 < w <= src_w and 0 < h <= src_h:
+                i = min(int(float(pos[s, 0]) * (src_h - h + 1)), src_h - h)
+                j = min(int(float(pos[s, 1]) * (src_w - w + 1)), src_w - w)
+                box = (i, j, h, w)
+                break
+        if box is None:     # torchvision's centre-crop fallback
+            in_ratio = src_w / src_h
+            if in_ratio < min(ratio):
+                w = src_w
+                h = int(round(w / min(ratio)))
+            elif in_ratio > max(ratio):
+                h = src_h
+                w = int(round(h * max(ratio)))
+            else:
+                w, h = src_w, src_h
+            box = ((src_h - h) // 2, (src_w - w) // 2, h, w)
+        theta = math.radians(-degrees + 2.0 * degrees * float(misc[s, 0]))
+        out[s, 0], out[s, 1], out[s, 2], out[s, 3] = box
+        out[s, 4], out[s, 5] = math.cos(theta), math.sin(theta)
+        out[s, 6] = 1.0 if float(misc[s, 1]) < 0.5 else 0.0
+    return out
+
+
+def val_params(n: int, src_h: int, src_w: int) -> torch.Tensor:
+    out = torch.zeros(n, PARAM_DIM, dtype=torch.float32)
+    out[:, 2], out[:, 3], out[:, 4] = src_h, src_w, 1.0
+    return out
+
+
+def resized_dims(train: bool, src_h: int, src_w: int, resize: int = DATA.resize) -> Tuple[int, int]:
+    """Size of the intermediate 'resized' image: 256x256 for train, shorter-side-256 for val."""
+    if train:
+        return resize, resize
+    if src_h <= src_w:
+        return resize, max(int(resize * src_w / src_h), 1)
+    return max(int(resize * src_h / src_w), 1), resize
+
+
+def augment_reference(src: torch.Tensor, params: torch.Tensor, resized_hw: Tuple[int, int],
+                      out_hw: int = DATA.crop, mean=DATA.mean, std=DATA.std) -> torch.Tensor:
+    """Torch evaluation of the fused transform.  src: uint8 [n,H,W,3] -> float32 [n,3,out,out]."""
+    n, H, W, _ = src.shape
+    RH, RW = resized_hw
+    dev = src.device
+    p = params.to(dev, torch.float32)
+    ys, xs = torch.meshgrid(torch.arange(out_hw, device=dev, dtype=torch.float32),
+                            torch.arange(out_hw, device=dev, dtype=torch.float32), indexing="ij")
+    # undo CenterCrop(out_hw) on the RH x RW image (torchvision rounds the offset)
+    off_y = int(round((RH - out_hw) / 2.0))
+    off_x = int(round((RW - out_hw) / 2.0))
+    ay = (ys + off_y).expand(n, -1, -1)
+    ax = (xs + off_x).expand(n, -1, -1)
+    flip = p[:, 6].view(n, 1, 1) > 0.5
+    bx = torch.where(flip, (RW - 1) - ax, ax)
+    by = ay
+    # undo rotation: PIL affine, output pixel centre -> input coordinate, nearest = floor
+    c, s = p[:, 4].view(n, 1, 1), p[:, 5].view(n, 1, 1)
+    cx, cy = RW / 2.0, RH / 2.0
+    dx, dy = bx + 0.5 - cx, by + 0.5 - cy
+    rx = torch.floor(c * dx - s * dy + cx)
+    ry = torch.floor(s * dx + c * dy + cy)
+    inside = (rx >= 0) & (rx < RW) & (ry >= 0) & (ry < RH)
+    # bilinear sample of the crop box (clamped to the box == resize of the cropped image)
+    top, left = p[:, 0].view(n, 1, 1), p[:, 1].view(n, 1, 1)
+    ch, cw = p[:, 2].view(n, 1, 1), p[:, 3].view(n, 1, 1)
+    sy = (ry + 0.5) * (ch / RH) - 0.5
+    sx = (rx + 0.5) * (cw / RW) - 0.5
+    sy = torch.minimum(torch.clamp(sy, min=0.0), ch - 1)
+    sx = torch.minimum(torch.clamp(sx, min=0.0), cw - 1)
+    y0, x0 = torch.floor(sy), torch.floor(sx)
+    wy, wx = (sy - y0), (sx - x0)
+    y1 = torch.minimum(y0 + 1, ch - 1)
+    x1 = torch.minimum(x0 + 1, cw - 1)
+    srcf = src.to(torch.float32)
+    bidx = torch.arange(n, device=dev).view(n, 1, 1).expand(-1, out_hw, out_hw)
+
+    def g(yy, xx):
+        return srcf[bidx, (yy + top).long().clamp_(0, H - 1), (xx + left).long().clamp_(0, W - 1)]
+
+    wy, wx = wy.unsqueeze(-1), wx.unsqueeze(-1)
+    val = (g(y0, x0) * (1 - wy) * (1 - wx) + g(y0, x1) * (1 - wy) * wx +
+           g(y1, x0) * wy * (1 - wx) + g(y1, x1) * wy * wx)
+    val = torch.where(inside.unsqueeze(-1), val, torch.zeros_like(val)) / 255.0
+    m = torch.tensor(mean, device=dev).view(1, 1, 1, 3)
+    sd = torch.tensor(std, device=dev).view(1, 1, 1, 3)
+    return ((val - m) / sd).permute(0, 3, 1, 2).contiguous()
+
+
+def reference_transforms(train: bool):
+    """The literal torchvision pipeline of the reference (distributedVggf.py:88-95 / :103-108)."""
+    from torchvision import transforms as T
+
+    norm = T.Normalize(list(DATA.mean), list(DATA.std))
+    if train:
+        return T.Compose([
+            T.RandomResizedCrop(size=DATA.resize, scale=DATA.crop_scale),
+            T.RandomRotation(degrees=DATA.rotation_deg),
+            T.RandomHorizontalFlip(),
+            T.CenterCrop(size=DATA.crop),
+            T.ToTensor(),
+            norm,
+        ])
+    return T.Compose([T.Resize(size=DATA.resize), T.CenterCrop(size=DATA.crop), T.ToTensor(), norm])

@@ -1,0 +1,94 @@
+"""Gradient bucket plan over a flat, ready-ordered arena.
+
+What the reference gets from torch DDP's C++ Reducer (distributedVggf.py:225): after
+the first iteration, parameters are regrouped in gradient-ready order into buckets capped at
+1 MiB (first) / 25 MiB (rest); a tensor larger than the cap sits alone (the 411 MB
+``classifier.0.weight`` gradient becomes one message).
+
+We own the plan instead.  Parameters are laid out in ONE flat arena in the order their gradients
+become ready (reverse of forward), every tensor aligned to ``align`` elements, and a bucket is
+simply a half-open element range ``[start, end)`` of that arena:
+  * no copy-in / copy-out: wgrad kernels write straight into the arena, the fused all-reduce
+    kernel reads and writes ranges of it;
+  * a tensor larger than the cap is *split* across several buckets so the reduction of the first
+    chunk overlaps with everything behind it (the reference cannot do that);
+  * bucket boundaries are multiples of ``align`` so every rank-slice of a two-shot / NVLS
+    reduction is 16-byte aligned for any world size up to 16.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Dict, List, Sequence, Tuple
+
+
+@dataclasses.dataclass(frozen=True)
+class Bucket:
+    index: int
+    start: int                 # element offset into the arena
+    end: int
+    tensors: Tuple[str, ...]   # names of tensors that overlap this range
+
+    @property
+    def numel(self) -> int:
+        return self.end - self.start
+
+
+@dataclasses.dataclass
+class BucketPlan:
+    offsets: Dict[str, int]        # tensor name -> element offset (ready order)
+    numels: Dict[str, int]
+    order: List[str]               # gradient-ready order
+    total: int                     # arena length in elements (aligned)
+    buckets: List[Bucket]
+    align: int
+
+    def bucket_of(self, name: str) -> List[int]:
+        return [b.index for b in self.buckets if name in b.tensors]
+
+    def last_tensor_of_bucket(self, b: Bucket) -> str:
+        """The tensor whose gradient completes the bucket (latest in ready order)."""
+        return max(b.tensors, key=self.order.index)
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def make_bucket_plan(ready_order: Sequence[Tuple[str, int]], cap_elems: int = 16 * 1024 * 1024,
+                     first_cap_elems: int = 0, align: int = 2048) -> BucketPlan:
+    """``ready_order``: (name, numel) in the order gradients are produced by backward."""
+    if cap_elems % align:
+        cap_elems = _round_up(cap_elems, align)
+    offsets, numels, order, pos = {}, {}, [], 0
+    for name, n in ready_order:
+        offsets[name], numels[name] = pos, n
+        order.append(name)
+        pos += _round_up(n, align)
+    total = pos
+
+    buckets: List[Bucket] = []
+    cur_start, cur_names = 0, []
+
+    def close(end: int) -> None:
+        nonlocal cur_start, cur_names
+        if end > cur_start:
+            buckets.append(Bucket(len(buckets), cur_start, end, tuple(cur_names)))
+        cur_start, cur_names = end, []
+
+    for name in order:
+        t0, t1 = offsets[name], offsets[name] + _round_up(numels[name], align)
+        cap = first_cap_elems if (first_cap_elems and not buckets) else cap_elems
+        if (t1 - t0) > cap:
+            close(t0)                       # flush what we have, then split the big tensor
+            p = t0
+            while p < t1:
+                q = min(p + cap, t1)
+                cur_names = [name]
+                close(q)
+                p = q
+            continue
+        if cur_names and (t1 - cur_start) > cap:
+            close(t0)
+        cur_names.append(name)
+    close(total)
+    return BucketPlan(offsets, numels, order, total, buckets, align)

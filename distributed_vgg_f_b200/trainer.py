@@ -1,0 +1,120 @@
+"""Training / evaluation loops.
+
+Reference (distributedVggf.py:126-197): ``Trainer(model, optimizer, train_loader, test_loader,
+device).fit(epochs)`` -- per batch: H2D, forward, cross-entropy, zero_grad, backward, step, two
+``.item()`` syncs; per epoch: a full (unsharded) validation pass on every rank and one report line
+``[Info] Epoch: e/E, train loss: .., train acc: ..%, test loss: .., test acc: ..%.``.
+
+``Trainer`` keeps the constructor, ``fit`` and the report line, for two interchangeable back ends:
+  * a torch ``nn.Module`` (optionally wrapped in ``parallel.ddp.FlatDDP``) -- the oracle / CPU path;
+  * ``engine.NativeEngine`` -- the sm_100a path, where forward, loss, backward, gradient
+    all-reduce and optimizer are one ``train_step`` call and metrics stay on the device.
+Differences kept on purpose: metrics accumulate on the device and are read once per epoch
+(``DeviceMeter``), ``set_epoch`` is called so shuffling changes between epochs, and throughput is
+reported on an extra line.
+"""
+from __future__ import annotations
+
+import time
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from .data.loader import FusedBatch
+from .utils.metrics import DeviceMeter
+
+
+def _is_native(model) -> bool:
+    return hasattr(model, "train_step") and hasattr(model, "eval_step")
+
+
+class Trainer:
+    def __init__(self, model, optimizer, train_loader, test_loader, device,
+                 class_weights: Optional[torch.Tensor] = None, verbose_throughput: bool = True,
+                 on_epoch_end=None) -> None:
+        self.model = model
+        self.optimizer = optimizer
+        self.train_loader = train_loader
+        self.test_loader = test_loader
+        self.device = device
+        # The reference carries a commented-out class-weighted loss (distributedVggf.py:164-166).
+        self.class_weights = class_weights.to(device) if class_weights is not None else None
+        self.verbose_throughput = verbose_throughput
+        self.on_epoch_end = on_epoch_end
+        self.history = []
+
+    # ------------------------------------------------------------------------------------------
+    def fit(self, epochs: int, start_epoch: int = 1) -> None:
+        for epoch in range(start_epoch, epochs + 1):
+            for ld in (self.train_loader, self.test_loader):
+                if hasattr(ld, "set_epoch"):
+                    ld.set_epoch(epoch - 1)
+            t0 = time.perf_counter()
+            train_loss, train_acc = self._train()
+            t1 = time.perf_counter()
+            test_loss, test_acc = self._evaluate()
+            print(
+                "[Info] Epoch: {}/{},".format(epoch, epochs),
+                "train loss: {}, train acc: {},".format(train_loss, train_acc),
+                "test loss: {}, test acc: {}.".format(test_loss, test_acc),
+                flush=True,
+            )
+            if self.verbose_throughput and train_loss.count:
+                print("[Perf] Epoch: {}/{}, train images/sec (this rank): {:.1f}".format(
+                    epoch, epochs, train_loss.count / max(t1 - t0, 1e-9)), flush=True)
+            self.history.append(dict(epoch=epoch, train_loss=train_loss.average,
+                                     train_acc=train_acc.accuracy, test_loss=test_loss.average,
+                                     test_acc=test_acc.accuracy))
+            if self.on_epoch_end is not None:
+                self.on_epoch_end(epoch, self)
+
+    # ------------------------------------------------------------------------------------------
+    def _to_device(self, batch):
+        if isinstance(batch, FusedBatch):
+            return batch.to_float(self.device)
+        inputs, targets = batch
+        return inputs.to(self.device, non_blocking=True), targets.to(self.device, non_blocking=True)
+
+    def _train(self):
+        meter = DeviceMeter(self.device)
+        if _is_native(self.model):
+            self.model.set_meter(meter)
+            for batch in self.train_loader:
+                self.model.train_step(batch)
+            self.model.sync()
+            return meter.snapshot()
+
+        self.model.train()
+        wrapper = self.model if hasattr(self.model, "finish_backward") else None
+        for batch in self.train_loader:
+            inputs, targets = self._to_device(batch)
+            outputs = self.model(inputs)
+            loss = F.cross_entropy(outputs, targets, weight=self.class_weights)
+            if wrapper is not None:
+                wrapper.zero_grad()
+            else:
+                self.optimizer.zero_grad()
+            loss.backward()
+            if wrapper is not None:
+                wrapper.finish_backward()
+            self.optimizer.step()
+            meter.add_reference(outputs.detach(), targets)
+        return meter.snapshot()
+
+    def _evaluate(self):
+        meter = DeviceMeter(self.device)
+        if _is_native(self.model):
+            self.model.set_meter(meter)
+            for batch in self.test_loader:
+                self.model.eval_step(batch)
+            self.model.sync()
+            return meter.snapshot()
+
+        self.model.eval()
+        with torch.no_grad():
+            for batch in self.test_loader:
+                inputs, targets = self._to_device(batch)
+                outputs = self.model(inputs)
+                meter.add_reference(outputs, targets)
+        return meter.snapshot()
