@@ -89,9 +89,9 @@ class VGGSpec:
         return total
 
 
-def _conv_specs() -> tuple:
+def _conv_specs(width_div: int = 1) -> tuple:
     convs, cin, idx = [], 3, 0
-    cfg = list(VGG16_CFG)
+    cfg = [v if v == "M" else max(int(v) // width_div, 8) for v in VGG16_CFG]
     for i, v in enumerate(cfg):
         if v == "M":
             idx += 1
@@ -126,7 +126,22 @@ def vgg16_spec(num_classes: int = 1000) -> VGGSpec:
     return VGGSpec(_conv_specs(), fcs, num_classes)
 
 
+def vggf_tiny_spec(num_classes: int) -> VGGSpec:
+    """Same topology as VGG-F at 1/8 width (test / CI model: exercises every code path in seconds)."""
+    convs = _conv_specs(8)
+    feat = convs[-1].cout * 7 * 7
+    fcs = (
+        FCSpec("classifier.0", feat, 128, True, 0.5),
+        FCSpec("classifier.3", 128, 128, True, 0.5),
+        FCSpec("classifier.6.0", 128, 32, True, 0.6, torch_default_init=True),
+        FCSpec("classifier.6.3", 32, num_classes, False, 0.0, torch_default_init=True),
+    )
+    return VGGSpec(convs, fcs, num_classes)
+
+
 def get_spec(model: str, num_classes: int) -> VGGSpec:
+    if model in ("vggf-tiny", "tiny"):
+        return vggf_tiny_spec(num_classes)
     if model in ("vggf", "vgg-f", "vgg_funnel"):
         return vggf_spec(num_classes)
     if model in ("vgg16", "vgg-16"):

@@ -1,0 +1,204 @@
+"""CPU-tier unit tests: CLI parity, metric arithmetic and formats, sampler
+arithmetic vs torch, ImageFolder discovery, model topology / parameter count / state-dict keys,
+bucket plan, transforms, checkpoint layout."""
+import math
+import os
+
+import pytest
+import torch
+
+import distributed_vgg_f_b200 as pkg
+from distributed_vgg_f_b200 import cli
+from distributed_vgg_f_b200.data import transforms as T
+from distributed_vgg_f_b200.data.folder import scan_image_folder
+from distributed_vgg_f_b200.data.loader import DataManager, FusedBatch
+from distributed_vgg_f_b200.data.sampler import ShardedSampler, shard_indices
+from distributed_vgg_f_b200.models.vggf import build_oracle, vgg16_spec, vggf_spec
+from distributed_vgg_f_b200.parallel.buckets import make_bucket_plan
+from distributed_vgg_f_b200.utils.metrics import Accuracy2, Average, DeviceMeter
+
+
+# ------------------------------------------------------------------------------------------- CLI
+def test_cli_flags_and_defaults(capsys):
+    args = cli.parse_command_line(["-iu", "tcp://127.0.0.1:1", "-rn", "0", "-ws", "1", "-rd", "/x"],
+                                  init=False)
+    assert (args.epochs, args.learning_rate, args.mini_batch, args.no_cuda) == (20, 0.001, 16, False)
+    assert args.init_url == "tcp://127.0.0.1:1" and args.rank == 0 and args.world_size == 1
+    assert "Namespace(" in capsys.readouterr().out          # the reference prints the namespace
+    args = cli.parse_command_line(["--init_url", "tcp://h:2", "--rank", "1", "--world_size", "2",
+                                   "--root_dir", "/d", "--epochs", "5", "--no_cuda",
+                                   "--learning_rate", "0.00001", "--mini_batch", "64"], init=False)
+    assert (args.epochs, args.learning_rate, args.mini_batch, args.no_cuda) == (5, 1e-5, 64, True)
+
+
+def test_cli_requires_root_dir():
+    with pytest.raises(SystemExit):
+        cli.parse_command_line(["-iu", "tcp://127.0.0.1:1", "-rn", "0", "-ws", "1"], init=False)
+    with pytest.raises(SystemExit):
+        cli.parse_command_line(["-rn", "0", "-ws", "1", "-rd", "/x"], init=False)
+
+
+# --------------------------------------------------------------------------------------- metrics
+def test_average_and_accuracy_formats():
+    a = Average()
+    a.update(2.0, 4)
+    a.update(1.0, 4)
+    assert a.average == 1.5 and str(a) == "1.500000"
+    acc = Accuracy2()
+    out = torch.tensor([[0.1, 0.9], [0.8, 0.2], [0.3, 0.7]])
+    acc.update(out, torch.tensor([1, 0, 0]))
+    assert acc.correct == 2 and acc.count == 3 and str(acc) == "66.67%"
+
+
+def test_device_meter_matches_host_metrics():
+    torch.manual_seed(0)
+    logits, tgt = torch.randn(10, 3), torch.randint(0, 3, (10,))
+    m = DeviceMeter("cpu")
+    m.add_reference(logits, tgt)
+    avg, acc = m.snapshot()
+    assert abs(avg.average - float(torch.nn.functional.cross_entropy(logits, tgt))) < 1e-6
+    assert acc.correct == int((logits.argmax(1) == tgt).sum())
+
+
+# --------------------------------------------------------------------------------------- sampler
+@pytest.mark.parametrize("n,ws", [(24, 2), (25, 2), (7, 4), (5760, 8), (3, 4)])
+def test_sampler_matches_torch_distributed_sampler(n, ws):
+    from torch.utils.data import DistributedSampler
+
+    ds = list(range(n))
+    for epoch in (0, 3):
+        for r in range(ws):
+            ref = DistributedSampler(ds, num_replicas=ws, rank=r, shuffle=True, seed=0)
+            ref.set_epoch(epoch)
+            assert shard_indices(n, ws, r, epoch=epoch) == list(iter(ref))
+    s = ShardedSampler(n, ws, 0, reference_order=True)
+    s.set_epoch(5)
+    assert list(iter(s)) == shard_indices(n, ws, 0, epoch=0)     # the reference never reshuffles
+
+
+# ------------------------------------------------------------------------------------------ data
+def test_imagefolder_contract(synth_root):
+    classes, samples = scan_image_folder(os.path.join(synth_root, "TrainData"))
+    assert classes == ["edible", "other", "toy"] and len(samples) == 24
+    from torchvision.datasets import ImageFolder
+
+    tv = ImageFolder(os.path.join(synth_root, "TrainData"))
+    assert tv.classes == classes and tv.samples == samples
+
+
+def test_datamanager_surface_and_batches(synth_root):
+    dm = DataManager(synth_root, 5, train=True)
+    assert dm.number_classes == 3 and dm.data_size == 24 and dm.class_names == ["edible", "other", "toy"]
+    batches = list(dm.get_loader())
+    assert [len(b.labels) for b in batches] == [5, 5, 5, 5, 4]      # ragged tail kept
+    assert isinstance(batches[0], FusedBatch) and batches[0].images_u8.shape == (5, 128, 128, 3)
+    x, y = batches[0].to_float()
+    assert x.shape == (5, 3, 224, 224) and x.dtype == torch.float32 and y.dtype == torch.int64
+    # sharded train / unsharded val (distributedVggf.py:115)
+    d0 = DataManager(synth_root, 4, train=True, world_size=2, rank=0)
+    d1 = DataManager(synth_root, 4, train=True, world_size=2, rank=1)
+    assert len(d0.get_loader()) == 3 and len(d1.get_loader()) == 3
+    v0 = DataManager(synth_root, 4, train=False, world_size=2, rank=0)
+    assert sum(len(b.labels) for b in v0.get_loader()) == 12
+
+
+def test_reference_pipeline_shapes(synth_root):
+    dm = DataManager(synth_root, 4, train=True, pipeline="reference")
+    x, y = next(iter(dm.get_loader()))
+    assert x.shape == (4, 3, 224, 224) and y.shape == (4,)
+
+
+def test_val_transform_matches_torchvision(synth_root):
+    """Resize(256)+CenterCrop(224)+Normalize: fused evaluation vs PIL, up to PIL's uint8 rounding."""
+    from PIL import Image
+
+    _, samples = scan_image_folder(os.path.join(synth_root, "ValidationData"))
+    img = Image.open(samples[0][0]).convert("RGB")
+    ref = T.reference_transforms(train=False)(img)
+    import numpy as np
+    src = torch.from_numpy(np.asarray(img)).unsqueeze(0)
+    got = T.augment_reference(src, T.val_params(1, 128, 128), (256, 256))[0]
+    assert float((got - ref).abs().max()) < 0.06     # 1-2 uint8 steps / std
+    assert float((got - ref).abs().mean()) < 0.01
+
+
+def test_train_params_distribution():
+    g = torch.Generator().manual_seed(0)
+    p = T.sample_train_params(500, 128, 128, g)
+    area = p[:, 2] * p[:, 3] / (128 * 128)
+    assert float(area.min()) > 0.75 and float(area.max()) <= 1.0
+    ang = torch.atan2(p[:, 5], p[:, 4]).abs() * 180 / math.pi
+    assert float(ang.max()) <= 10.0 + 1e-4
+    assert 0.4 < float(p[:, 6].mean()) < 0.6
+    assert bool(((p[:, 0] + p[:, 2]) <= 128).all() and ((p[:, 1] + p[:, 3]) <= 128).all())
+
+
+# ----------------------------------------------------------------------------------------- model
+def test_vggf_topology_and_param_count():
+    spec = vggf_spec(3)
+    assert spec.num_params == 136_359_747
+    assert vgg16_spec(1000).num_params == 138_357_544
+    assert len(spec.param_names) == 34
+    assert abs(spec.flops_per_image(224) / 1e9 - 30.94) < 0.05
+    assert abs(spec.flops_per_image(128) / 1e9 - 10.27) < 0.35   # avgpool upsample not counted
+
+
+def test_oracle_state_dict_keys_match_torchvision():
+    from torch import nn
+    from torchvision import models
+
+    tv = models.vgg16(weights=None)
+    tv.classifier[6] = nn.Sequential(nn.Linear(4096, 512), nn.ReLU(inplace=True), nn.Dropout(0.6),
+                                     nn.Linear(512, 3))        # distributedVggf.py:52-57
+    with torch.device("meta"):
+        ours = pkg.models.vggf.VGGOracle.__new__(pkg.models.vggf.VGGOracle)
+    ours = build_oracle(vggf_spec(3), seed=0)
+    ref_sd, our_sd = tv.state_dict(), ours.state_dict()
+    assert list(ref_sd.keys()) == list(our_sd.keys())
+    assert all(ref_sd[k].shape == our_sd[k].shape for k in ref_sd)
+    tv.load_state_dict(our_sd)                                   # interoperable
+    x = torch.randn(1, 3, 64, 64)
+    tv.eval(), ours.eval()
+    assert torch.allclose(tv(x), ours(x), atol=1e-5)
+
+
+def test_vgg_funnel_model_factory_is_dropin():
+    m = pkg.vgg_funnel_model(5, seed=0)
+    assert m.classifier[6][3].out_features == 5 and m.classifier[6][2].p == 0.6
+
+
+# --------------------------------------------------------------------------------------- buckets
+def test_bucket_plan_covers_arena_and_splits_big_tensors():
+    spec = vggf_spec(3)
+    ready = [(n, math.prod(spec.param_shape(n))) for n in reversed(spec.param_names)]
+    plan = make_bucket_plan(ready, cap_elems=8 * 1024 * 1024)
+    assert plan.buckets[0].start == 0 and plan.buckets[-1].end == plan.total
+    for a, b in zip(plan.buckets, plan.buckets[1:]):
+        assert a.end == b.start
+    assert all(b.start % plan.align == 0 and b.end % plan.align == 0 for b in plan.buckets)
+    assert max(b.numel for b in plan.buckets) <= 8 * 1024 * 1024
+    big = plan.bucket_of("classifier.0.weight")
+    assert len(big) == math.ceil(102_760_448 / (8 * 1024 * 1024))     # split, unlike DDP
+    assert plan.order[0] == "classifier.6.3.bias" and plan.order[-1] == "features.0.weight"
+    # every tensor lies inside the union of its buckets
+    for n in plan.order:
+        ids = plan.bucket_of(n)
+        assert plan.buckets[ids[0]].start <= plan.offsets[n]
+        assert plan.buckets[ids[-1]].end >= plan.offsets[n] + plan.numels[n]
+
+
+# ------------------------------------------------------------------------------------ checkpoint
+def test_checkpoint_layout_roundtrip(tmp_path):
+    from distributed_vgg_f_b200.utils import checkpoint as ck
+
+    m = build_oracle(vggf_spec(3), seed=1)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    path = str(tmp_path / "c.pt")
+    ck.save_checkpoint(path, m, opt, epoch=2, args={"mini_batch": 4})
+    payload = torch.load(path, weights_only=False)
+    assert payload["format"] == ck.FORMAT and payload["epoch"] == 2
+    keys = list(payload["model"].keys())
+    assert len(keys) == 34 and keys[0] == "module.features.0.weight" and keys[-1] == "module.classifier.6.3.bias"
+    m2 = build_oracle(vggf_spec(3), seed=2)
+    assert ck.load_checkpoint(path, m2, None) == 2
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
