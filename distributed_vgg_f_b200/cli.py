@@ -59,7 +59,7 @@ def build_parser() -> argparse.ArgumentParser:
                         help="Mini-batch size. The default value is {}".format(TRAIN.mini_batch))
 
     ext = parser.add_argument_group("extensions (not in the reference)")
-    ext.add_argument("--model", default="vggf", choices=["vggf", "vgg16", "vggf-tiny"])
+    ext.add_argument("--model", default="vggf", choices=["vggf", "vgg16", "vggf-tiny", "vggf-mini"])
     ext.add_argument("--num-classes", type=int, default=None,
                      help="override the class count (default: number of class folders)")
     ext.add_argument("--engine", default="auto", choices=["auto", "native", "oracle"],

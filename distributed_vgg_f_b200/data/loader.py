@@ -36,6 +36,7 @@ class FusedBatch(NamedTuple):
     params: torch.Tensor        # float32 [mb, 8]     (same)
     labels: torch.Tensor        # int64 [mb]          (same)
     resized_hw: Tuple[int, int]
+    state: Optional[dict] = None    # consumer may set state["event"]: slot is reusable after it fires
 
     def to_float(self, device="cpu") -> Tuple[torch.Tensor, torch.Tensor]:
         """Evaluate the fused transform with torch ops (CPU / oracle path)."""
@@ -84,10 +85,12 @@ class _FusedLoader:
         H, W = cache.src_hw
         self.resized_hw = T.resized_dims(train, H, W)
         self._ring = []
+        self._state = []
         for _ in range(prefetch + 1):
             self._ring.append((self._buf((mb, H, W, 3), torch.uint8),
                                self._buf((mb, T.PARAM_DIM), torch.float32),
                                self._buf((mb,), torch.int64)))
+            self._state.append({})
 
     def _buf(self, shape, dtype):
         t = torch.empty(shape, dtype=dtype)
@@ -126,6 +129,9 @@ class _FusedLoader:
                 sel = torch.tensor(idx[b0:b0 + self.mb], dtype=torch.int64)
                 k = len(sel)
                 slot = free.get()
+                ev = self._state[slot].pop("event", None)
+                if ev is not None:
+                    ev.synchronize()        # async H2D of the previous occupant has finished
                 img, par, lab = self._ring[slot]
                 torch.index_select(self.cache.images, 0, sel, out=img[:k])
                 torch.index_select(self.cache.labels, 0, sel, out=lab[:k])
@@ -146,7 +152,7 @@ class _FusedLoader:
             slot, k = item
             img, par, lab = self._ring[slot]
             prev = slot
-            yield FusedBatch(img[:k], par[:k], lab[:k], self.resized_hw)
+            yield FusedBatch(img[:k], par[:k], lab[:k], self.resized_hw, self._state[slot])
         th.join()
 
 

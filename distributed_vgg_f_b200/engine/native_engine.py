@@ -1,0 +1,495 @@
+"""NativeEngine: the whole training step on hand-written sm_100a kernels.
+
+Where the reference's hot loop (distributedVggf.py:158-175) is ``model(inputs)`` ->
+``cross_entropy`` -> ``zero_grad`` -> ``backward`` (DDP hooks all-reduce buckets) -> ``Adam.step``
+-> two ``.item()`` syncs, all delegated to cuDNN / cuBLAS / c10d / ATen, this engine owns every
+stage:
+
+  input     fused augment kernel: uint8 HWC -> normalised bf16 im2col rows of the first conv
+  forward   conv0 = tcgen05 GEMM on the im2col rows; conv1..12 = tcgen05 implicit GEMM (4-D TMA
+            boxes, TMEM accumulators, bias+ReLU epilogue); max-pool; FC stack = swap-AB split-K
+            tcgen05 GEMMs + bias/ReLU/Philox-dropout epilogue; fused cross-entropy (+ metrics)
+  backward  FC wgrad/dgrad GEMMs (MN-major operands, no transposed copies), conv dgrad with the
+            ReLU mask fused in the epilogue, fused ReLU+pool backward, conv wgrad split-K with
+            fp32 red.add straight into the flat gradient arena
+  reduce    per bucket, as soon as its last gradient is enqueued: fused pack(fp32->bf16, 1/ws) +
+            one-shot / two-shot / NVLS reduction over peer memory on a high-priority side stream
+  update    fused Adam/SGD on the bucket right behind its reduction (reads the reduced bf16 wire,
+            writes fp32 master + bf16 shadow, zeroes the gradient range)
+Nothing synchronises with the host inside a step; loss / accuracy accumulate in a device meter.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from ..config import DATA, TRAIN
+from ..data.loader import FusedBatch
+from ..models import layout as L
+from ..models.vggf import VGGSpec, build_oracle
+from ..parallel.buckets import BucketPlan, make_bucket_plan
+from ..parallel.process_group import distributed_is_initialized
+from ..utils.metrics import DeviceMeter
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class PhaseTimer:
+    """CUDA-event timers around the phases of a step (``--profile events``)."""
+
+    def __init__(self, enabled: bool) -> None:
+        self.enabled = enabled
+        self.pending: List[Tuple[str, torch.cuda.Event, torch.cuda.Event]] = []
+        self.totals: Dict[str, float] = {}
+        self.counts: Dict[str, int] = {}
+        self._open: Dict[str, torch.cuda.Event] = {}
+
+    def start(self, name: str) -> None:
+        if self.enabled:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._open[name] = e
+
+    def stop(self, name: str) -> None:
+        if self.enabled and name in self._open:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.pending.append((name, self._open.pop(name), e))
+
+    def collect(self) -> Dict[str, float]:
+        for name, a, b in self.pending:
+            b.synchronize()
+            self.totals[name] = self.totals.get(name, 0.0) + a.elapsed_time(b)
+            self.counts[name] = self.counts.get(name, 0) + 1
+        self.pending.clear()
+        return {k: self.totals[k] / max(self.counts[k], 1) for k in self.totals}
+
+
+class NativeEngine:
+    def __init__(self, spec: VGGSpec, device: torch.device, batch: int, lr: float = TRAIN.learning_rate,
+                 optimizer: str = "adam", momentum: float = TRAIN.momentum, weight_decay: float = 0.0,
+                 compute_dtype: str = "bf16", allreduce: str = "auto", wire_dtype: str = "bf16",
+                 bucket_mb: float = 32.0, seed: int = 0, pretrained_state: Optional[dict] = None,
+                 profile: Optional[str] = None, input_hw: int = DATA.crop, comm_ctas: int = 16,
+                 init_state: Optional[Dict[str, torch.Tensor]] = None, unpack_fp32: bool = False) -> None:
+        ops.require()
+        if compute_dtype != "bf16":
+            raise NotImplementedError("the native engine computes in bf16 with fp32 master weights; "
+                                      "use --engine oracle for fp32 numerics")
+        for c in spec.convs[1:]:
+            if c.cin % 64 or c.cout % 64:
+                raise ValueError("native conv kernels need channel counts that are multiples of 64")
+        if spec.convs[0].cout % 64 or spec.convs[0].cin != 3:
+            raise ValueError("first conv must be 3 -> multiple of 64 channels")
+        self.spec, self.device, self.B = spec, torch.device(device), int(batch)
+        self.lr, self.opt_name, self.momentum, self.weight_decay = lr, optimizer, momentum, weight_decay
+        self.beta1, self.beta2, self.eps = TRAIN.adam_beta1, TRAIN.adam_beta2, TRAIN.adam_eps
+        self.seed, self.HW = int(seed), int(input_hw)
+        self.step_count = 0
+        self.train_dropout = True        # tests switch dropout off to compare gradients exactly
+        self.apply_updates = True        # False: leave raw gradients in g32 (gradient inspection)
+        self.meter: Optional[DeviceMeter] = None
+        self.timer = PhaseTimer(profile == "events")
+        self.nvtx = profile == "nvtx"
+        self.world = dist.get_world_size() if distributed_is_initialized() else 1
+        self.rank = dist.get_rank() if distributed_is_initialized() else 0
+        self.ar_algo, self.comm_ctas, self.unpack_fp32 = allreduce, comm_ctas, unpack_fp32
+        self.use_nccl = allreduce == "nccl"
+        dev = self.device
+
+        # ---- flat arenas (gradient-ready order) --------------------------------------------------
+        cap = int(bucket_mb * 1024 * 1024 / 4)
+        self.plan: BucketPlan = make_bucket_plan(L.ready_order(spec), cap_elems=cap)
+        n = self.plan.total
+        self.p32 = torch.zeros(n, dtype=F32, device=dev)
+        self.g32 = torch.zeros(n, dtype=F32, device=dev)
+        self.m32 = torch.zeros(n, dtype=F32, device=dev)
+        self.v32 = torch.zeros(n, dtype=F32, device=dev) if optimizer == "adam" else None
+        self.w16 = torch.zeros(n, dtype=BF16, device=dev)
+
+        if init_state is None:
+            init_state = build_oracle(spec, seed=seed, pretrained_state=pretrained_state).state_dict()
+        self.import_state(init_state, sync=False)
+
+        # ---- cross-GPU plumbing ------------------------------------------------------------------
+        self.arena = None
+        self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)
+        if self.world > 1 and not self.use_nccl:
+            from ..parallel.symm import SymmetricArena
+
+            wdt = BF16 if wire_dtype == "bf16" else F32
+            self.arena = SymmetricArena(n, dev, wire_dtype=wdt)
+        if self.world > 1:
+            self._broadcast_params()
+
+        self._build_buffers()
+
+    # ============================================================================ parameters
+    def _view(self, arena: torch.Tensor, name: str) -> torch.Tensor:
+        off = self.plan.offsets[name]
+        return arena[off:off + self.plan.numels[name]].view(L.native_shape(self.spec, name))
+
+    def import_state(self, state: Dict[str, torch.Tensor], sync: bool = True) -> None:
+        """Load torch-layout tensors (checkpoint / oracle state dict) into the arenas."""
+        with torch.no_grad():
+            for name in self.spec.param_names:
+                t = state[name].detach().to(self.device, F32)
+                self._view(self.p32, name).copy_(L.to_native(self.spec, name, t))
+            ops.require().cast_to_bf16(self.p32, self.w16)
+        if sync and self.world > 1:
+            self._broadcast_params()
+
+    def export_state(self) -> Dict[str, torch.Tensor]:
+        return {name: L.to_torch(self.spec, name, self._view(self.p32, name)).detach().cpu()
+                for name in self.spec.param_names}
+
+    def export_optimizer_state(self) -> dict:
+        st = {"name": self.opt_name, "step": self.step_count, "lr": self.lr}
+        if self.opt_name == "adam":
+            st["exp_avg"] = {n: L.to_torch(self.spec, n, self._view(self.m32, n)).cpu() for n in self.spec.param_names}
+            st["exp_avg_sq"] = {n: L.to_torch(self.spec, n, self._view(self.v32, n)).cpu() for n in self.spec.param_names}
+        else:
+            st["momentum_buffer"] = {n: L.to_torch(self.spec, n, self._view(self.m32, n)).cpu()
+                                     for n in self.spec.param_names}
+        return st
+
+    def import_optimizer_state(self, st: dict) -> None:
+        self.step_count = int(st.get("step", 0))
+        with torch.no_grad():
+            for key, arena in (("exp_avg", self.m32), ("exp_avg_sq", self.v32), ("momentum_buffer", self.m32)):
+                if key in st and arena is not None:
+                    for n, t in st[key].items():
+                        self._view(arena, n).copy_(L.to_native(self.spec, n, t.to(self.device, F32)))
+
+    def set_lr(self, lr: float) -> None:
+        self.lr = lr
+
+    def _broadcast_params(self) -> None:
+        """DDP's constructor sync (distributedVggf.py:225): everybody adopts rank 0's weights."""
+        if self.arena is not None:
+            self.arena.broadcast_(self.p32, root=0)
+        else:
+            dist.broadcast(self.p32, src=0)
+        ops.require().cast_to_bf16(self.p32, self.w16)
+        torch.cuda.synchronize(self.device)
+
+    # ============================================================================== buffers
+    def _build_buffers(self) -> None:
+        spec, B, dev, HW = self.spec, self.B, self.device, self.HW
+        # double-buffered device-side input staging, filled by a copy stream
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self._in_slot = 0
+        self._src_u8 = [None, None]
+        self._params_dev = [torch.zeros(B, 8, dtype=F32, device=dev) for _ in range(2)]
+        self._labels_dev = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(2)]
+        self._in_free = [None, None]           # event: the step that used this slot is done with it
+        self.labels_dev = self._labels_dev[0]
+        self.col0 = torch.empty(B * HW * HW, L.CONV0_K, dtype=BF16, device=dev)
+        self.x_nhwc = None
+        self.acts: List[torch.Tensor] = []      # post-ReLU conv outputs
+        self.pools: List[Optional[torch.Tensor]] = []
+        h = HW
+        for c in spec.convs:
+            self.acts.append(torch.empty(B, h, h, c.cout, dtype=BF16, device=dev))
+            if c.pool_after:
+                h //= 2
+                self.pools.append(torch.empty(B, h, h, c.cout, dtype=BF16, device=dev))
+            else:
+                self.pools.append(None)
+        self.feat_hw = h
+        cl = spec.convs[-1].cout
+        ph = spec.pooled_hw
+        assert spec.fcs[0].fin == cl * ph * ph, "classifier.0 must consume the pooled feature map"
+        self.avg = None if h == ph else torch.empty(B, ph, ph, cl, dtype=BF16, device=dev)
+        # FC stack
+        self.fc_acc = [torch.zeros(B, f.fout, dtype=F32, device=dev) for f in spec.fcs]
+        self.fc_y = [torch.empty(B, f.fout, dtype=BF16, device=dev) if i < len(spec.fcs) - 1 else None
+                     for i, f in enumerate(spec.fcs)]
+        self.fc_dacc = [torch.zeros(B, f.fin, dtype=F32, device=dev) for f in spec.fcs]
+        self.fc_dz = [torch.zeros(B, _round_up(f.fout, 8), dtype=BF16, device=dev) for f in spec.fcs]
+        self.logits = torch.zeros(B, spec.num_classes, dtype=F32, device=dev)
+        self.loss_buf = torch.zeros(1, dtype=F32, device=dev)
+        self.scratch_meter = torch.zeros(4, dtype=F32, device=dev)
+        # backward activations-gradients: two ping-pong buffers big enough for the largest map
+        biggest = max(a.numel() for a in self.acts)
+        self.dbuf = [torch.empty(biggest, dtype=BF16, device=dev) for _ in range(2)]
+        self.dfeat = torch.empty(B, ph, ph, cl, dtype=BF16, device=dev)
+
+    # ================================================================================ inputs
+    def _stage_input(self, batch) -> int:
+        """Copy a batch to the device and produce the first conv's im2col rows.  Returns b."""
+        C = ops.require()
+        HW = self.HW
+        j = self._in_slot
+        self._in_slot ^= 1
+        self.labels_dev = self._labels_dev[j]
+        cur = torch.cuda.current_stream(self.device)
+        if isinstance(batch, FusedBatch):
+            b = int(batch.labels.shape[0])
+            src = batch.images_u8
+            if self._src_u8[j] is None or self._src_u8[j].shape[1:] != src.shape[1:]:
+                self._src_u8[j] = torch.empty((self.B,) + tuple(src.shape[1:]), dtype=torch.uint8,
+                                              device=self.device)
+            with torch.cuda.stream(self.copy_stream):
+                if self._in_free[j] is not None:
+                    self.copy_stream.wait_event(self._in_free[j])
+                self._src_u8[j][:b].copy_(src, non_blocking=True)
+                self._params_dev[j][:b].copy_(batch.params, non_blocking=True)
+                self._labels_dev[j][:b].copy_(batch.labels, non_blocking=True)
+                h2d = torch.cuda.Event()
+                h2d.record(self.copy_stream)
+            if batch.state is not None:
+                batch.state["event"] = h2d          # the loader may refill the pinned slot after this
+            cur.wait_event(h2d)
+            ops.augment(self._src_u8[j][:b], self._params_dev[j][:b], self.col0[:b * HW * HW],
+                        batch.resized_hw, out_hw=HW, mode="im2col", pad=L.CONV0_K)
+            return b
+        x, y = batch
+        b = int(y.shape[0])
+        x = x.to(self.device, F32, non_blocking=True).contiguous()
+        assert x.shape[2] == HW and x.shape[3] == HW, "input size differs from the engine's input_hw"
+        self.labels_dev[:b].copy_(y, non_blocking=True)
+        if self.x_nhwc is None:
+            self.x_nhwc = torch.empty(self.B, HW, HW, 4, dtype=BF16, device=self.device)
+        C.nchw_to_nhwc(x, self.x_nhwc[:b])
+        C.im2col_c3(self.x_nhwc[:b], self.col0[:b * HW * HW], L.CONV0_K)
+        return b
+
+    def _release_input(self) -> None:
+        """The augment kernel and the loss have consumed the staged batch: its slot may be refilled."""
+        ev = torch.cuda.Event()
+        ev.record()
+        self._in_free[self._in_slot ^ 1] = ev
+
+    # =============================================================================== forward
+    def _w(self, name: str) -> torch.Tensor:
+        return self._view(self.w16, name + ".weight")
+
+    def _b(self, name: str) -> torch.Tensor:
+        return self._view(self.p32, name + ".bias")
+
+    @staticmethod
+    def _ksplit(m_tiles: int, k_iters: int, target: int = 256) -> int:
+        return max(1, min(k_iters, target // max(m_tiles, 1)))
+
+    def _forward(self, b: int, train: bool) -> None:
+        C = ops.require()
+        spec, HW = self.spec, self.HW
+        c0 = spec.convs[0]
+        M0 = b * HW * HW
+        # conv0: im2col GEMM with fused bias + ReLU -> bf16 NHWC
+        ops.gemm(self.col0[:M0], self._w(c0.name), self.acts[0][:b].view(M0, c0.cout), M=M0, N=c0.cout,
+                 K=L.CONV0_K, epi="bf16_bias_relu", bias=self._b(c0.name), bn=64 if c0.cout == 64 else 0)
+        x = self.acts[0][:b]
+        if c0.pool_after:
+            x = ops.maxpool2x2(x, out=self.pools[0][:b])
+        for i, c in enumerate(spec.convs[1:], start=1):
+            y = self.acts[i][:b]
+            C.conv_fprop(x, self._w(c.name), self._b(c.name), y, True, 0)
+            x = y
+            if c.pool_after:
+                x = ops.maxpool2x2(y, out=self.pools[i][:b])
+        if self.avg is not None:
+            x = ops.adaptive_avgpool(x, spec.pooled_hw, spec.pooled_hw, out=self.avg[:b])
+        self.feat = x
+        h = x.reshape(b, -1)
+        last = len(spec.fcs) - 1
+        for i, f in enumerate(spec.fcs):
+            m_tiles = (f.fout + 127) // 128
+            ks = self._ksplit(m_tiles, (f.fin + 63) // 64)
+            acc = self.fc_acc[i][:b]
+            ops.gemm(self._w(f.name), h, acc, M=f.fout, N=b, K=f.fin, epi="f32_atomic_t", ksplit=ks, ldo=f.fout)
+            if i == last:
+                ops.fc_bias_act(acc, self._b(f.name), None, self.logits[:b], B=b, N=f.fout, relu=False)
+            else:
+                p = f.dropout if (train and self.train_dropout) else 0.0
+                ops.fc_bias_act(acc, self._b(f.name), self.fc_y[i][:b], None, B=b, N=f.fout, relu=f.relu,
+                                drop_p=p, seed=self.seed * 1000003 + i, offset=self.step_count)
+                h = self.fc_y[i][:b]
+
+    # ============================================================================== backward
+    def _grad(self, name: str) -> torch.Tensor:
+        return self._view(self.g32, name)
+
+    def _backward(self, b: int) -> None:
+        C = ops.require()
+        spec = self.spec
+        fcs, convs = spec.fcs, spec.convs
+        last = len(fcs) - 1
+        # ---- FC stack ----------------------------------------------------------------------
+        for i in range(last, -1, -1):
+            f = fcs[i]
+            ld = self.fc_dz[i].shape[1]
+            dz = self.fc_dz[i][:b]                                   # [b][ld] bf16, cols >= fout are 0
+            x_in = self.fc_y[i - 1][:b] if i > 0 else self.feat.reshape(b, -1)
+            ops.bias_grad(dz, self._grad(f.name + ".bias"), b, f.fout, ld=ld)
+            self._bucket_done(f.name + ".bias")
+            # wgrad: dW[fout][fin] = dz^T x_in   (both operands MN-major: stored [K=b][*])
+            ops.gemm(dz, x_in, self._grad(f.name + ".weight"), M=f.fout, N=f.fin, K=b, a_mn=True, b_mn=True,
+                     epi="f32_store", ldo=f.fin)
+            # dgrad: dX[b][fin] = dz W ; swap-AB with W read MN-major (stored [K=fout][M=fin])
+            m_tiles = (f.fin + 127) // 128
+            ks = self._ksplit(m_tiles, (f.fout + 63) // 64)
+            dacc = self.fc_dacc[i][:b]
+            ops.gemm(self._w(f.name), dz, dacc, M=f.fin, N=b, K=f.fout, a_mn=True,
+                     epi="f32_atomic_t" if ks > 1 else "f32_store_t", ksplit=ks, ldo=f.fin)
+            # only now may the optimizer touch W_i: the dgrad above still reads the old weights
+            self._bucket_done(f.name + ".weight")
+            if i > 0:
+                prev = fcs[i - 1]
+                ops.fc_grad_act(dacc, self.fc_y[i - 1][:b], self.fc_dz[i - 1][:b], B=b, N=f.fin,
+                                relu=prev.relu, drop_p=prev.dropout if self.train_dropout else 0.0)
+            else:
+                ops.fc_grad_act(dacc, None, self.dfeat[:b].view(b, -1), B=b, N=f.fin, relu=False)
+        # ---- feature map gradient ------------------------------------------------------------
+        g = self.dfeat[:b]
+        if self.avg is not None:
+            g = ops.adaptive_avgpool_bwd(g, self.feat_hw, self.feat_hw,
+                                         out=self.dbuf[1][:b * self.feat_hw ** 2 * convs[-1].cout]
+                                         .view(b, self.feat_hw, self.feat_hw, convs[-1].cout))
+        # ---- conv stack ----------------------------------------------------------------------
+        # invariant at loop entry: if layer i pools, `g` is dP_i (grad wrt pooled output);
+        # otherwise `g` is dZ_i (grad wrt the pre-ReLU output, mask already applied).
+        pp = 0
+        for i in range(len(convs) - 1, -1, -1):
+            c = convs[i]
+            y = self.acts[i][:b]
+            if c.pool_after:
+                dz = self.dbuf[pp][:y.numel()].view_as(y)
+                ops.maxpool2x2_relu_bwd(y, g, out=dz)
+                pp ^= 1
+            else:
+                dz = g
+            M = y.numel() // c.cout
+            ops.bias_grad(dz.view(M, c.cout), self._grad(c.name + ".bias"), M, c.cout)
+            self._bucket_done(c.name + ".bias")
+            if i == 0:
+                ks = max(1, min(M // 64, 296))
+                ops.gemm(dz.view(M, c.cout), self.col0[:M], self._grad(c.name + ".weight"), M=c.cout,
+                         N=L.CONV0_K, K=M, a_mn=True, b_mn=True, epi="f32_atomic", ksplit=ks, ldo=L.CONV0_K)
+                self._bucket_done(c.name + ".weight")
+                break
+            x_in = self.pools[i - 1][:b] if convs[i - 1].pool_after else self.acts[i - 1][:b]
+            C.conv_wgrad(dz, x_in, self._grad(c.name + ".weight"), 1.0, 0, 0)
+            dx = self.dbuf[pp][:x_in.numel()].view_as(x_in)
+            # ReLU backward of layer i-1 is fused here unless a pool sits in between
+            C.conv_dgrad(dz, self._w(c.name), None if convs[i - 1].pool_after else x_in, dx, 0)
+            self._bucket_done(c.name + ".weight")      # after dgrad: it reads the pre-update weights
+            pp ^= 1
+            g = dx
+
+    # ================================================================= all-reduce + optimizer
+    def _begin_step(self) -> None:
+        self._missing = [len(bk.tensors) for bk in self.plan.buckets]
+        self._tensor_buckets = getattr(self, "_tensor_buckets", None) or \
+            {n: self.plan.bucket_of(n) for n in self.plan.order}
+
+    def _bucket_done(self, name: str) -> None:
+        """Called right after the kernels producing ``name``'s gradient were enqueued."""
+        for bi in self._tensor_buckets[name]:
+            self._missing[bi] -= 1
+            if self._missing[bi] == 0:
+                self._reduce_and_update(bi)
+
+    def _apply_update(self, s: int, e: int, g16: Optional[torch.Tensor]) -> None:
+        g32 = None if g16 is not None else self.g32[s:e]
+        if self.opt_name == "adam":
+            ops.adam_step(self.p32[s:e], self.m32[s:e], self.v32[s:e], g32=g32, g16=g16, shadow=self.w16[s:e],
+                          lr=self.lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps,
+                          weight_decay=self.weight_decay, step=self.step_count, zero=self.g32[s:e])
+        else:
+            ops.sgd_step(self.p32[s:e], self.m32[s:e], g32=g32, g16=g16, shadow=self.w16[s:e], lr=self.lr,
+                         momentum=self.momentum, weight_decay=self.weight_decay,
+                         first=(self.step_count == 1), zero=self.g32[s:e])
+
+    def _reduce_and_update(self, bi: int) -> None:
+        bk = self.plan.buckets[bi]
+        s, e = bk.start, bk.end
+        if not self.apply_updates:
+            return
+        if self.world == 1:
+            self._apply_update(s, e, None)       # same stream, right behind the producing kernels
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            if self.use_nccl:                    # library baseline (comparison only)
+                self.g32[s:e].mul_(1.0 / self.world)
+                dist.all_reduce(self.g32[s:e])
+                self._apply_update(s, e, None)
+                return
+            algo = self.arena.pick_algo(e - s, self.ar_algo)
+            to_f32 = algo == "oneshot" or self.unpack_fp32 or self.arena.wire_dtype == F32
+            self.arena.allreduce(self.g32, self.g32 if to_f32 else None, s, e - s, algo=algo,
+                                 slot=bi % self.arena.slots, max_ctas=self.comm_ctas)
+            self._apply_update(s, e, None if to_f32 else self.arena.wire[s:e])
+
+    def _end_step(self) -> None:
+        if self.world > 1:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+
+    # ================================================================================ public
+    def set_meter(self, meter: Optional[DeviceMeter]) -> None:
+        self.meter = meter
+
+    def train_step(self, batch) -> torch.Tensor:
+        """One optimisation step.  Returns the device scalar holding this batch's mean loss."""
+        self.step_count += 1
+        t = self.timer
+        if self.nvtx:
+            torch.cuda.nvtx.range_push("step")
+        t.start("input")
+        b = self._stage_input(batch)
+        t.stop("input")
+        t.start("forward")
+        self._forward(b, train=True)
+        ld = self.fc_dz[-1].shape[1]
+        meter = self.meter.buf if self.meter is not None else self.scratch_meter
+        ops.cross_entropy(self.logits[:b], self.labels_dev[:b], self.fc_dz[-1][:b], ld, meter, self.loss_buf)
+        self._release_input()
+        t.stop("forward")
+        t.start("backward+reduce+update")
+        self._begin_step()
+        self._backward(b)
+        self._end_step()
+        t.stop("backward+reduce+update")
+        if self.nvtx:
+            torch.cuda.nvtx.range_pop()
+        return self.loss_buf
+
+    def eval_step(self, batch) -> torch.Tensor:
+        b = self._stage_input(batch)
+        self._forward(b, train=False)
+        meter = self.meter.buf if self.meter is not None else self.scratch_meter
+        ops.cross_entropy(self.logits[:b], self.labels_dev[:b], None, 0, meter, self.loss_buf)
+        self._release_input()
+        return self.loss_buf
+
+    def forward_logits(self, batch) -> torch.Tensor:
+        b = self._stage_input(batch)
+        self._forward(b, train=False)
+        self._release_input()
+        return self.logits[:b].clone()
+
+    def sync(self) -> None:
+        torch.cuda.synchronize(self.device)
+
+    def phase_times(self) -> Dict[str, float]:
+        return self.timer.collect()
+
+    # torch-module-like conveniences used by Trainer / checkpoint
+    def train(self) -> None:
+        pass
+
+    def eval(self) -> None:
+        pass

@@ -139,9 +139,24 @@ def vggf_tiny_spec(num_classes: int) -> VGGSpec:
     return VGGSpec(convs, fcs, num_classes)
 
 
+def vggf_mini_spec(num_classes: int) -> VGGSpec:
+    """VGG-F topology with every conv at 64 channels and a narrow head: the smallest network the
+    native tcgen05 kernels accept (channel counts must be multiples of 64); GPU test model."""
+    convs = tuple(ConvSpec(c.name, 3 if i == 0 else 64, 64, c.pool_after) for i, c in enumerate(_conv_specs()))
+    fcs = (
+        FCSpec("classifier.0", 64 * 7 * 7, 256, True, 0.5),
+        FCSpec("classifier.3", 256, 256, True, 0.5),
+        FCSpec("classifier.6.0", 256, 64, True, 0.6, torch_default_init=True),
+        FCSpec("classifier.6.3", 64, num_classes, False, 0.0, torch_default_init=True),
+    )
+    return VGGSpec(convs, fcs, num_classes)
+
+
 def get_spec(model: str, num_classes: int) -> VGGSpec:
     if model in ("vggf-tiny", "tiny"):
         return vggf_tiny_spec(num_classes)
+    if model in ("vggf-mini", "mini"):
+        return vggf_mini_spec(num_classes)
     if model in ("vggf", "vgg-f", "vgg_funnel"):
         return vggf_spec(num_classes)
     if model in ("vgg16", "vgg-16"):

@@ -1,0 +1,137 @@
+"""NativeEngine (sm_100a kernels end to end) against the torch oracle on the same weights."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _mk(batch=4, hw=64, classes=3, seed=0, **kw):
+    from distributed_vgg_f_b200.engine.native_engine import NativeEngine
+    from distributed_vgg_f_b200.models.vggf import build_oracle, vggf_mini_spec
+
+    spec = vggf_mini_spec(classes)
+    oracle = build_oracle(spec, seed=seed)
+    # the engine computes with bf16 weights: give the oracle the same rounded values
+    with torch.no_grad():
+        for p in oracle.parameters():
+            if p.dim() > 1:
+                p.copy_(p.to(torch.bfloat16).float())
+    eng = NativeEngine(spec, device=torch.device(DEV), batch=batch, lr=1e-3, seed=seed, input_hw=hw,
+                       init_state=oracle.state_dict(), **kw)
+    return spec, oracle.to(DEV), eng
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12))
+
+
+def test_forward_matches_oracle():
+    spec, oracle, eng = _mk()
+    torch.manual_seed(1)
+    x = torch.randn(4, 3, 64, 64, device=DEV).to(torch.bfloat16).float()
+    y = torch.randint(0, 3, (4,), device=DEV)
+    oracle.eval()
+    with torch.no_grad():
+        ref = oracle(x)
+    got = eng.forward_logits((x, y))
+    assert _rel(got, ref) < 3e-2
+
+
+def test_ragged_batch_and_eval_step():
+    spec, oracle, eng = _mk(batch=8)
+    from distributed_vgg_f_b200.utils.metrics import DeviceMeter
+
+    torch.manual_seed(2)
+    x = torch.randn(5, 3, 64, 64, device=DEV).to(torch.bfloat16).float()
+    y = torch.randint(0, 3, (5,), device=DEV)
+    meter = DeviceMeter(DEV)
+    eng.set_meter(meter)
+    eng.eval_step((x, y))
+    avg, acc = meter.snapshot()
+    oracle.eval()
+    with torch.no_grad():
+        ref = oracle(x)
+    assert acc.count == 5 and abs(avg.average - float(F.cross_entropy(ref, y))) < 3e-2
+
+
+def test_gradients_match_autograd():
+    from distributed_vgg_f_b200.models import layout as L
+
+    spec, oracle, eng = _mk()
+    eng.train_dropout = False
+    eng.apply_updates = False
+    torch.manual_seed(3)
+    x = torch.randn(4, 3, 64, 64, device=DEV).to(torch.bfloat16).float()
+    y = torch.randint(0, 3, (4,), device=DEV)
+    oracle.eval()                                  # dropout off, same as the engine here
+    loss = F.cross_entropy(oracle(x), y)
+    loss.backward()
+    got_loss = float(eng.train_step((x, y)))
+    assert abs(got_loss - float(loss)) < 3e-2
+    worst = {}
+    for name, p in oracle.named_parameters():
+        ref = L.to_native(spec, name, p.grad)
+        got = eng._view(eng.g32, name)
+        worst[name] = _rel(got, ref)
+    bad = {k: v for k, v in worst.items() if v > 0.08}
+    assert not bad, bad
+
+
+def test_training_reduces_loss_and_updates_shadow():
+    spec, oracle, eng = _mk(batch=8)
+    from distributed_vgg_f_b200.data import transforms as T
+    from distributed_vgg_f_b200.data.loader import FusedBatch
+    from distributed_vgg_f_b200.data.synthetic import synthetic_uint8_batch
+
+    imgs, labels = synthetic_uint8_batch(8, 128, 3, seed=0)
+    batch = FusedBatch(torch.from_numpy(imgs).pin_memory(), T.val_params(8, 128, 128).pin_memory(),
+                       torch.from_numpy(labels).pin_memory(), (73, 73), None)   # 64x64 centre crop of a 73x73 resize
+    eng.train_dropout = False
+    losses = [float(eng.train_step(batch)) for _ in range(40)]
+    assert all(math.isfinite(v) for v in losses)
+    assert losses[-1] < 0.5 * losses[0], losses[::8]
+    assert torch.equal(eng.w16.float(), eng.p32.to(torch.bfloat16).float())     # shadow follows master
+    assert torch.count_nonzero(eng.g32) == 0                                    # optimizer zeroed the arena
+
+
+def test_fused_input_path_equals_float_path():
+    spec, oracle, eng = _mk()
+    from distributed_vgg_f_b200.data import transforms as T
+    from distributed_vgg_f_b200.data.loader import FusedBatch
+    from distributed_vgg_f_b200.data.synthetic import synthetic_uint8_batch
+
+    imgs, labels = synthetic_uint8_batch(4, 128, 3, seed=5)
+    src = torch.from_numpy(imgs)
+    params = T.sample_train_params(4, 128, 128, torch.Generator().manual_seed(1))
+    batch = FusedBatch(src, params, torch.from_numpy(labels), (80, 80), None)
+    a = eng.forward_logits(batch)
+    x = T.augment_reference(src.to(DEV), params, (80, 80), out_hw=64)
+    b = eng.forward_logits((x, torch.from_numpy(labels).to(DEV)))
+    assert _rel(a, b) < 2e-2
+
+
+def test_checkpoint_roundtrip_with_oracle(tmp_path):
+    from distributed_vgg_f_b200.models.vggf import build_oracle
+    from distributed_vgg_f_b200.utils import checkpoint as ck
+
+    spec, oracle, eng = _mk()
+    path = str(tmp_path / "e.pt")
+    ck.save_checkpoint(path, eng, None, epoch=1)
+    payload = torch.load(path, weights_only=False)
+    assert list(payload["model"].keys())[0] == "module.features.0.weight"
+    fresh = build_oracle(spec, seed=123)
+    fresh.load_state_dict(ck.strip_module_prefix(payload["model"]))          # reference-style consumer
+    for (k, a), (_, b) in zip(fresh.state_dict().items(), oracle.state_dict().items()):
+        assert torch.allclose(a, b.cpu(), atol=0, rtol=0), k
+    spec2, _, eng2 = _mk(seed=7)
+    assert ck.load_checkpoint(path, eng2, None) == 1
+    assert torch.equal(eng2.p32, eng.p32)
+
+
+def test_full_vggf_smoke():
+    import __graft_entry__ as g
+    g.smoke()
