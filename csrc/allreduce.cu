@@ -126,8 +126,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) allreduce_kernel(const ArArgs a
     for (long long v = chunk0 + threadIdx.x; v < chunk1; v += AR_THREADS) {
       if constexpr (WIRE32) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int p = 0; p < world; ++p) {
-          const int peer = (rank + p) % world;
+        for (int peer = 0; peer < world; ++peer) {   // fixed order: bit-identical sums on every rank
           const uint4 raw = ld_v4(reinterpret_cast<const uint8_t*>(c.wire_ptrs[peer]) + a.start * 4 + v * 16);
           acc.x += __uint_as_float(raw.x); acc.y += __uint_as_float(raw.y);
           acc.z += __uint_as_float(raw.z); acc.w += __uint_as_float(raw.w);
@@ -135,10 +134,8 @@ __global__ void __launch_bounds__(AR_THREADS, 1) allreduce_kernel(const ArArgs a
         *reinterpret_cast<float4*>(out + v * 4) = acc;
       } else {
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int p = 0; p < world; ++p) {
-          const int peer = (rank + p) % world;
+        for (int peer = 0; peer < world; ++peer)
           accum_bf16x8(acc, ld_v4(reinterpret_cast<const uint8_t*>(c.wire_ptrs[peer]) + a.start * 2 + v * 16));
-        }
         *reinterpret_cast<float4*>(out + v * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         *reinterpret_cast<float4*>(out + v * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
       }

@@ -80,7 +80,8 @@ class NativeEngine:
                  compute_dtype: str = "bf16", allreduce: str = "auto", wire_dtype: str = "bf16",
                  bucket_mb: float = 32.0, seed: int = 0, pretrained_state: Optional[dict] = None,
                  profile: Optional[str] = None, input_hw: int = DATA.crop, comm_ctas: int = 16,
-                 init_state: Optional[Dict[str, torch.Tensor]] = None, unpack_fp32: bool = False) -> None:
+                 init_state: Optional[Dict[str, torch.Tensor]] = None, unpack_fp32: bool = False,
+                 distributed: bool = True) -> None:
         ops.require()
         if compute_dtype != "bf16":
             raise NotImplementedError("the native engine computes in bf16 with fp32 master weights; "
@@ -100,8 +101,8 @@ class NativeEngine:
         self.meter: Optional[DeviceMeter] = None
         self.timer = PhaseTimer(profile == "events")
         self.nvtx = profile == "nvtx"
-        self.world = dist.get_world_size() if distributed_is_initialized() else 1
-        self.rank = dist.get_rank() if distributed_is_initialized() else 0
+        self.world = dist.get_world_size() if (distributed and distributed_is_initialized()) else 1
+        self.rank = dist.get_rank() if (distributed and distributed_is_initialized()) else 0
         self.ar_algo, self.comm_ctas, self.unpack_fp32 = allreduce, comm_ctas, unpack_fp32
         self.use_nccl = allreduce == "nccl"
         dev = self.device
@@ -414,10 +415,9 @@ class NativeEngine:
     def _reduce_and_update(self, bi: int) -> None:
         bk = self.plan.buckets[bi]
         s, e = bk.start, bk.end
-        if not self.apply_updates:
-            return
         if self.world == 1:
-            self._apply_update(s, e, None)       # same stream, right behind the producing kernels
+            if self.apply_updates:
+                self._apply_update(s, e, None)   # same stream, right behind the producing kernels
             return
         ev = torch.cuda.Event()
         ev.record()
@@ -426,13 +426,16 @@ class NativeEngine:
             if self.use_nccl:                    # library baseline (comparison only)
                 self.g32[s:e].mul_(1.0 / self.world)
                 dist.all_reduce(self.g32[s:e])
-                self._apply_update(s, e, None)
+                if self.apply_updates:
+                    self._apply_update(s, e, None)
                 return
             algo = self.arena.pick_algo(e - s, self.ar_algo)
-            to_f32 = algo == "oneshot" or self.unpack_fp32 or self.arena.wire_dtype == F32
+            to_f32 = (algo == "oneshot" or self.unpack_fp32 or self.arena.wire_dtype == F32
+                      or not self.apply_updates)
             self.arena.allreduce(self.g32, self.g32 if to_f32 else None, s, e - s, algo=algo,
                                  slot=bi % self.arena.slots, max_ctas=self.comm_ctas)
-            self._apply_update(s, e, None if to_f32 else self.arena.wire[s:e])
+            if self.apply_updates:
+                self._apply_update(s, e, None if to_f32 else self.arena.wire[s:e])
 
     def _end_step(self) -> None:
         if self.world > 1:

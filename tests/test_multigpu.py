@@ -1,0 +1,127 @@
+"""Collective + data-parallel equivalence tests on >= 2 GPUs of one node (SURVEY section 4 tiers
+"Collective unit" and "DDP equivalence").  Each test spawns one process per GPU."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(fn, world, *args):
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mp.spawn(_entry, args=(world, port, fn, args), nprocs=world, join=True)
+
+
+def _entry(rank, world, port, fn, args):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        fn(rank, world, *args)
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------ all-reduce
+def _allreduce_worker(rank, world, wire_fp32):
+    import torch.distributed as dist
+
+    from distributed_vgg_f_b200.parallel.symm import SymmetricArena
+
+    dev = torch.device("cuda", rank)
+    n_max = 1 << 24
+    arena = SymmetricArena(n_max, dev, wire_dtype=torch.float32 if wire_fp32 else torch.bfloat16)
+    algos = ["oneshot", "twoshot"] + (["nvls"] if arena.has_multicast else [])
+    torch.manual_seed(100 + rank)
+    for algo in algos:
+        for n, start in [(8, 0), (8 * 1000, 2048), (1 << 20, 0), ((1 << 22) + 8 * 37, 4096), (n_max - 8192, 8192)]:
+            for it in range(3):                       # back-to-back: flag / wire reuse
+                g = torch.randn(n_max, device=dev)
+                out = torch.zeros(n_max, device=dev)
+                out.copy_(g)
+                scaled = g[start:start + n] / world
+                if not wire_fp32:
+                    scaled = scaled.to(torch.bfloat16).float()
+                ref = scaled.clone()
+                dist.all_reduce(ref)
+                used = arena.allreduce(g, out, start, n, algo=algo, slot=it % 4, max_ctas=16)
+                assert used == algo
+                torch.cuda.synchronize(dev)
+                got = out[start:start + n]
+                tol = 1e-5 if wire_fp32 else 1e-2       # result rounded to bf16 once on the wire
+                err = float((got - ref).abs().max() / (ref.abs().max() + 1e-9))
+                assert err < tol, (algo, n, it, err)
+                # untouched outside the range
+                assert torch.equal(out[:start], g[:start]) and torch.equal(out[start + n:], g[start + n:])
+                if algo != "oneshot":                   # wire holds the same reduced values on every rank
+                    w = arena.wire[start:start + n].float()
+                    assert float((w - ref).abs().max() / (ref.abs().max() + 1e-9)) < tol
+    # broadcast
+    data = torch.full((100003 * 4,), float(rank + 1), device=dev)
+    arena.broadcast_(data, root=0)
+    torch.cuda.synchronize(dev)
+    assert float(data.min()) == 1.0 and float(data.max()) == 1.0
+
+
+@pytest.mark.parametrize("wire_fp32", [False, True])
+def test_fused_allreduce_matches_nccl(wire_fp32):
+    _run(_allreduce_worker, min(torch.cuda.device_count(), 8), wire_fp32)
+
+
+# ---------------------------------------------------------------------------------- engine DDP
+def _engine_worker(rank, world, algo):
+    from distributed_vgg_f_b200.engine.native_engine import NativeEngine
+    from distributed_vgg_f_b200.models.vggf import build_oracle, vggf_mini_spec
+
+    dev = torch.device("cuda", rank)
+    spec = vggf_mini_spec(3)
+    # every rank starts from DIFFERENT weights: the constructor broadcast must fix that
+    init = build_oracle(spec, seed=rank).state_dict()
+    eng = NativeEngine(spec, device=dev, batch=4, lr=1e-3, seed=0, input_hw=64, init_state=init, allreduce=algo,
+                       bucket_mb=0.25)
+    ref_init = build_oracle(spec, seed=0).state_dict()
+    single = NativeEngine(spec, device=dev, batch=4 * world, lr=1e-3, seed=0, input_hw=64, init_state=ref_init,
+                          distributed=False)
+    assert torch.equal(eng.p32, single.p32), "rank-0 weights were not broadcast"
+    for e in (eng, single):
+        e.train_dropout = False
+        e.apply_updates = False
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(4 * world, 3, 64, 64, generator=g).to(torch.bfloat16).float()
+    y = torch.randint(0, 3, (4 * world,), generator=g)
+    eng.train_step((x[4 * rank:4 * rank + 4], y[4 * rank:4 * rank + 4]))
+    single.train_step((x, y))
+    eng.sync()
+    a, r = eng.g32, single.g32
+    cos = float(torch.dot(a, r) / (a.norm() * r.norm()))
+    assert cos > 0.995, cos      # bf16 wire + different batch split of the bf16 activations
+    # and a real optimisation step keeps all replicas identical
+    eng.apply_updates = True
+    eng.g32.zero_()
+    eng.train_step((x[4 * rank:4 * rank + 4], y[4 * rank:4 * rank + 4]))
+    eng.sync()
+    import torch.distributed as dist
+    ref = eng.p32.clone()
+    dist.broadcast(ref, src=0)
+    assert torch.equal(ref, eng.p32), "replicas diverged after an update"
+
+
+@pytest.mark.parametrize("algo", ["auto", "twoshot", "oneshot"])
+def test_engine_data_parallel_equivalence(algo):
+    _run(_engine_worker, 2, algo)
