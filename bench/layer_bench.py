@@ -64,8 +64,11 @@ for i, c in enumerate(spec.convs):
             t = timeit(lambda: C.conv_fprop(x, w, bias, y, True, bn))
             rows.append(("%s fprop %dx%d %d->%d bn%d" % (c.name, h, h, c.cin, c.cout, bn), t, fl, 0))
         for bn in ([64] if c.cin == 64 else [128, 256] if c.cin >= 256 else [128]):
-            t = timeit(lambda: C.conv_dgrad(dz, w, x, dx, bn))
+            t = timeit(lambda: C.conv_dgrad(dz, w, x, dx, None, bn))
             rows.append(("%s dgrad bn%d" % (c.name, bn), t, fl, 0))
+            cs = torch.zeros(c.cin, device=dev)
+            t = timeit(lambda: C.conv_dgrad(dz, w, x, dx, cs, bn))
+            rows.append(("%s dgrad+colsum bn%d" % (c.name, bn), t, fl, 0))
         for bn in ([64] if c.cin == 64 else [128, 256] if c.cin >= 256 else [128]):
             t = timeit(lambda: C.conv_wgrad(dz, x, dw, 1.0, 0, bn))
             rows.append(("%s wgrad bn%d" % (c.name, bn), t, fl, 0))
@@ -85,6 +88,9 @@ for i, c in enumerate(spec.convs):
             rows.append(("%s maxpool fwd" % c.name, t, 0, y.numel() * 2 * 1.25 / 1e9))
             t = timeit(lambda: ops.maxpool2x2_relu_bwd(y, p, out=dz))
             rows.append(("%s pool+relu bwd" % c.name, t, 0, y.numel() * 2 * 2.25 / 1e9))
+            cs2 = torch.zeros(c.cout, device=dev)
+            t = timeit(lambda: ops.maxpool2x2_relu_bwd(y, p, out=dz, colsum=cs2))
+            rows.append(("%s pool+relu bwd+colsum" % c.name, t, 0, y.numel() * 2 * 2.25 / 1e9))
         t = timeit(lambda: ops.bias_grad(dz.view(-1, c.cout), torch.zeros(c.cout, device=dev), B * h * h, c.cout))
         rows.append(("%s bias_grad" % c.name, t, 0, dz.numel() * 2 / 1e9))
         del x, y, dz, dx
@@ -122,7 +128,12 @@ from distributed_vgg_f_b200.data import transforms as T
 prm = T.sample_train_params(B, 128, 128).to(dev)
 col = torch.empty(B * HW * HW, 64, dtype=torch.bfloat16, device=dev)
 t = timeit(lambda: ops.augment(src, prm, col, (256, 256), mode="im2col", pad=64))
-rows.append(("augment -> im2col", t, 0, col.numel() * 2 / 1e9))
+rows.append(("augment -> im2col (one pass)", t, 0, col.numel() * 2 / 1e9))
+x4 = torch.empty(B, HW, HW, 4, dtype=torch.bfloat16, device=dev)
+t = timeit(lambda: ops.augment(src, prm, x4, (256, 256), mode="nhwc", pad=4))
+rows.append(("augment -> NHWC4", t, 0, x4.numel() * 2 / 1e9))
+t = timeit(lambda: ops.require().im2col_c3(x4, col, 64))
+rows.append(("NHWC4 -> im2col", t, 0, col.numel() * 2 / 1e9))
 
 out = []
 tot_native = 0.0

@@ -70,38 +70,53 @@ __global__ void augment_nhwc_kernel(const uint8_t* __restrict__ src, const float
     float v[3];
     aug_sample(src + static_cast<long long>(n) * g.SH * g.SW * 3, params + n * 8, g, oy, ox, v);
     bf16* o = out + i * pad;
-    o[0] = __float2bfloat16(v[0]);
-    o[1] = __float2bfloat16(v[1]);
-    o[2] = __float2bfloat16(v[2]);
-    for (int c = 3; c < pad; ++c) o[c] = __float2bfloat16(0.f);
+    if (pad == 4) {          // one 8-byte store per pixel
+      *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], 0.f));
+    } else {
+      o[0] = __float2bfloat16(v[0]);
+      o[1] = __float2bfloat16(v[1]);
+      o[2] = __float2bfloat16(v[2]);
+      for (int c = 3; c < pad; ++c) o[c] = __float2bfloat16(0.f);
+    }
   }
 }
 
-// mode 1: im2col rows for the 3x3/pad-1 first convolution.  One thread per (pixel, tap): it
-// evaluates the transform at the tap's neighbour (or 0 outside the image: conv zero padding acts
-// on the *normalised* tensor) and writes 3 bf16; tap 9 writes the zero tail [27, kpad).
+// mode 1: im2col rows for the 3x3/pad-1 first convolution.  One thread per (pixel, 8-element
+// chunk of the row): it evaluates the transform at the (up to 4) taps its chunk covers (0 outside
+// the image: conv zero padding acts on the *normalised* tensor) and issues ONE 16-byte store, so a
+// warp writes 512 contiguous bytes.  Chunks beyond k = 27 are the zero tail.
 __global__ void augment_im2col_kernel(const uint8_t* __restrict__ src, const float* __restrict__ params,
                                       bf16* __restrict__ out, AugGeom g, int kpad) {
-  const long long total = static_cast<long long>(g.N) * g.OH * g.OW * 10;
+  const int chunks = kpad / 8;
+  const long long total = static_cast<long long>(g.N) * g.OH * g.OW * chunks;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int tap = i % 10;
-    const long long pix = i / 10;
-    bf16* row = out + pix * kpad;
-    if (tap == 9) {
-      for (int k = 27; k < kpad; ++k) row[k] = __float2bfloat16(0.f);
-      continue;
+    const int chunk = static_cast<int>(i % chunks);
+    const long long pix = i / chunks;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int k0 = chunk * 8;
+    if (k0 < 27) {
+      const int ox = pix % g.OW;
+      const int oy = (pix / g.OW) % g.OH;
+      const int n = static_cast<int>(pix / (static_cast<long long>(g.OW) * g.OH));
+      const uint8_t* img = src + static_cast<long long>(n) * g.SH * g.SW * 3;
+      const float* prm = params + n * 8;
+      const int tap_lo = k0 / 3;
+      const int tap_hi = min((k0 + 7) / 3, 8);
+      for (int tap = tap_lo; tap <= tap_hi; ++tap) {
+        const int yy = oy + tap / 3 - 1, xx = ox + tap % 3 - 1;
+        float s3[3] = {0.f, 0.f, 0.f};
+        if (yy >= 0 && yy < g.OH && xx >= 0 && xx < g.OW) aug_sample(img, prm, g, yy, xx, s3);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int k = tap * 3 + c - k0;
+          if (k >= 0 && k < 8) v[k] = s3[c];
+        }
+      }
     }
-    const int ox = pix % g.OW;
-    const int oy = (pix / g.OW) % g.OH;
-    const int n = static_cast<int>(pix / (static_cast<long long>(g.OW) * g.OH));
-    const int yy = oy + tap / 3 - 1, xx = ox + tap % 3 - 1;
-    float v[3] = {0.f, 0.f, 0.f};
-    if (yy >= 0 && yy < g.OH && xx >= 0 && xx < g.OW)
-      aug_sample(src + static_cast<long long>(n) * g.SH * g.SW * 3, params + n * 8, g, yy, xx, v);
-    row[tap * 3 + 0] = __float2bfloat16(v[0]);
-    row[tap * 3 + 1] = __float2bfloat16(v[1]);
-    row[tap * 3 + 2] = __float2bfloat16(v[2]);
+    const uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(out + pix * kpad + k0) = pk;
   }
 }
 
@@ -116,8 +131,8 @@ void augment_fused(const uint8_t* src, const float* params, bf16* out, int N, in
     const int blocks = static_cast<int>((pixels + 255) / 256 < 148 * 16 ? (pixels + 255) / 256 : 148 * 16);
     augment_nhwc_kernel<<<blocks, 256, 0, s>>>(src, params, out, g, pad);
   } else {
-    if (pad < 27) throw std::runtime_error("[b200] augment_fused: kpad must be >= 27");
-    const long long total = pixels * 10;
+    if (pad < 32 || pad % 8) throw std::runtime_error("[b200] augment_fused: kpad must be a multiple of 8, >= 32");
+    const long long total = pixels * (pad / 8);
     const int blocks = static_cast<int>((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
     augment_im2col_kernel<<<blocks, 256, 0, s>>>(src, params, out, g, pad);
   }
@@ -125,36 +140,45 @@ void augment_fused(const uint8_t* src, const float* params, bf16* out, int N, in
   check_last("augment_fused");
 }
 
-// im2col of an already-normalised NHWC (C padded to cpad) bf16 image -- the path used when the
-// caller supplies float tensors (reference pipeline, tests) instead of uint8 + parameters.
+// im2col of an already-normalised NHWC (3 channels padded to cpad = 4) bf16 image: the second half
+// of the two-pass input path (augment -> 8-byte pixels, 25 MB, stays in L2 -> im2col rows).  One
+// thread per (pixel, 8-element chunk): up to four 8-byte pixel loads, one 16-byte store.
 __global__ void im2col3x3_c3_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W,
                                     int cpad, int kpad) {
-  const long long total = static_cast<long long>(N) * H * W * 10;
+  const int chunks = kpad / 8;
+  const long long total = static_cast<long long>(N) * H * W * chunks;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int tap = i % 10;
-    const long long pix = i / 10;
-    bf16* row = out + pix * kpad;
-    if (tap == 9) {
-      for (int k = 27; k < kpad; ++k) row[k] = __float2bfloat16(0.f);
-      continue;
+    const int chunk = static_cast<int>(i % chunks);
+    const long long pix = i / chunks;
+    const int k0 = chunk * 8;
+    uint32_t h[8];                                   // bf16 bit patterns, compile-time indexed only
+    if (k0 < 27) {
+      const int w = pix % W;
+      const int hh = (pix / W) % H;
+      const long long img = (pix / (static_cast<long long>(W) * H)) * H * W;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = k0 + e;
+        const int tap = k / 3, c = k - 3 * tap;
+        const int yy = hh + tap / 3 - 1, xx = w + tap % 3 - 1;
+        uint2 px = make_uint2(0u, 0u);
+        if (k < 27 && yy >= 0 && yy < H && xx >= 0 && xx < W)
+          px = __ldg(reinterpret_cast<const uint2*>(x + (img + static_cast<long long>(yy) * W + xx) * 4));
+        h[e] = c == 0 ? (px.x & 0xffffu) : (c == 1 ? (px.x >> 16) : (px.y & 0xffffu));
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h[e] = 0u;
     }
-    const int w = pix % W;
-    const int h = (pix / W) % H;
-    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-    const int yy = h + tap / 3 - 1, xx = w + tap % 3 - 1;
-    const bf16 z = __float2bfloat16(0.f);
-    bf16 v0 = z, v1 = z, v2 = z;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-      const bf16* p = x + ((static_cast<long long>(n) * H + yy) * W + xx) * cpad;
-      v0 = p[0]; v1 = p[1]; v2 = p[2];
-    }
-    row[tap * 3 + 0] = v0; row[tap * 3 + 1] = v1; row[tap * 3 + 2] = v2;
+    const uint4 pk = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+    *reinterpret_cast<uint4*>(out + pix * kpad + k0) = pk;
   }
 }
 
 void im2col3x3_c3(const bf16* x, bf16* out, int N, int H, int W, int cpad, int kpad, cudaStream_t s) {
-  const long long total = static_cast<long long>(N) * H * W * 10;
+  if (cpad != 4 || kpad % 8 || kpad < 32) throw std::runtime_error("[b200] im2col3x3_c3: cpad must be 4, kpad a multiple of 8 >= 32");
+  const long long total = static_cast<long long>(N) * H * W * (kpad / 8);
   const int blocks = static_cast<int>((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
   im2col3x3_c3_kernel<<<blocks, 256, 0, s>>>(x, out, N, H, W, cpad, kpad);
   count_launch();

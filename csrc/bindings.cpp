@@ -42,12 +42,12 @@ static void conv_fprop(const at::Tensor& x, const at::Tensor& w, c10::optional<a
   b200::conv3x3_fprop(bfp(x), bfp(w), f32p_opt(bias), bfp_mut(y), N, H, W, Cin, Cout, relu, (int)bn, cur_stream());
 }
 static void conv_dgrad(const at::Tensor& dz, const at::Tensor& w, c10::optional<at::Tensor> mask, at::Tensor dx,
-                       int64_t bn) {
+                       c10::optional<at::Tensor> colsum, int64_t bn) {
   c10::cuda::CUDAGuard g(dz.device());
   TORCH_CHECK(dz.dim() == 4 && dz.is_contiguous() && w.is_contiguous() && dx.is_contiguous(), "conv_dgrad: contiguous NHWC");
   const int N = dz.size(0), H = dz.size(1), W = dz.size(2), Cout = dz.size(3), Cin = dx.size(3);
   TORCH_CHECK(w.numel() == (int64_t)Cout * 9 * Cin, "conv_dgrad: weight shape mismatch");
-  b200::conv3x3_dgrad(bfp(dz), bfp(w), bfp_opt(mask), bfp_mut(dx), N, H, W, Cin, Cout, (int)bn, cur_stream());
+  b200::conv3x3_dgrad(bfp(dz), bfp(w), bfp_opt(mask), bfp_mut(dx), f32p_opt(colsum), N, H, W, Cin, Cout, (int)bn, cur_stream());
 }
 static void conv_wgrad(const at::Tensor& dz, const at::Tensor& x, at::Tensor dw, double scale, int64_t ksplit,
                        int64_t bn) {
@@ -58,14 +58,23 @@ static void conv_wgrad(const at::Tensor& dz, const at::Tensor& x, at::Tensor dw,
   b200::conv3x3_wgrad(bfp(dz), bfp(x), f32p(dw), N, H, W, Cin, Cout, (float)scale, (int)ksplit, (int)bn, cur_stream());
 }
 
+static void shift_probe(const at::Tensor& A, const at::Tensor& B, at::Tensor out, int64_t shift, int64_t pitch,
+                        bool use_base_offset, int64_t mode) {
+  c10::cuda::CUDAGuard g(A.device());
+  b200::umma_shift_probe(bfp(A), (int)A.size(0), bfp(B), f32p(out), (int)shift, (int)pitch, use_base_offset ? 1 : 0,
+                         (int)mode, cur_stream());
+}
+
 // ------------------------------------------------------------------------------------ element-wise
 static void maxpool_fwd(const at::Tensor& x, at::Tensor y) {
   c10::cuda::CUDAGuard g(x.device());
   b200::maxpool2x2_fwd(bfp(x), bfp_mut(y), x.size(0), x.size(1), x.size(2), x.size(3), cur_stream());
 }
-static void maxpool_relu_bwd(const at::Tensor& y, const at::Tensor& dp, at::Tensor dz) {
+static void maxpool_relu_bwd(const at::Tensor& y, const at::Tensor& dp, at::Tensor dz,
+                             c10::optional<at::Tensor> colsum) {
   c10::cuda::CUDAGuard g(y.device());
-  b200::maxpool2x2_relu_bwd(bfp(y), bfp(dp), bfp_mut(dz), y.size(0), y.size(1), y.size(2), y.size(3), cur_stream());
+  b200::maxpool2x2_relu_bwd(bfp(y), bfp(dp), bfp_mut(dz), f32p_opt(colsum), y.size(0), y.size(1), y.size(2), y.size(3),
+                            cur_stream());
 }
 static void avgpool_fwd(const at::Tensor& x, at::Tensor y) {
   c10::cuda::CUDAGuard g(x.device());
@@ -181,6 +190,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "distributed-vgg-f_b200 native sm_100a kernels";
   m.def("launch_count", &b200::launch_count);
   m.def("gemm", &gemm);
+  m.def("shift_probe", &shift_probe);
   m.def("conv_fprop", &conv_fprop);
   m.def("conv_dgrad", &conv_dgrad);
   m.def("conv_wgrad", &conv_wgrad);

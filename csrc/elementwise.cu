@@ -74,11 +74,21 @@ void maxpool2x2_fwd(const bf16* x, bf16* y, int N, int H, int W, int C, cudaStre
 }
 
 // Backward of [ReLU -> maxpool2x2] in one pass: the gradient of a window goes to its first
-// maximal element (torch's tie rule) and only if that maximum is positive (ReLU mask).
+// maximal element (torch's tie rule) and only if that maximum is positive (ReLU mask).  Optionally
+// also accumulates colsum[c] += sum of dz over pixels (the conv layer's bias gradient): the grid
+// stride is a multiple of C/8, so a thread always sees the same 8 channels and keeps them in
+// registers; one shared-memory reduction and C global atomics per block at the end.
 __global__ void maxpool2x2_relu_bwd_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dp,
-                                           bf16* __restrict__ dz, int N, int H, int W, int C) {
+                                           bf16* __restrict__ dz, float* __restrict__ colsum, int N, int H,
+                                           int W, int C) {
+  extern __shared__ float s_sum[];      // [C] when colsum
   const int OH = H / 2, OW = W / 2, C8 = C / 8;
   const long long total = static_cast<long long>(N) * OH * OW * C8;
+  float bsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (colsum) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_sum[i] = 0.f;
+    __syncthreads();
+  }
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c8 = i % C8;
@@ -104,20 +114,31 @@ __global__ void maxpool2x2_relu_bwd_kernel(const bf16* __restrict__ y, const bf1
       const bool ic = !ia && !ib && c[k] == m;
       const bool id = !ia && !ib && !ic;
       ra[k] = ia ? gg : 0.f; rb[k] = ib ? gg : 0.f; rc[k] = ic ? gg : 0.f; rd[k] = id ? gg : 0.f;
+      bsum[k] += gg;
     }
     *reinterpret_cast<uint4*>(dz + o00) = pack8(ra);
     *reinterpret_cast<uint4*>(dz + o00 + C) = pack8(rb);
     *reinterpret_cast<uint4*>(dz + o00 + rowstride) = pack8(rc);
     *reinterpret_cast<uint4*>(dz + o00 + rowstride + C) = pack8(rd);
   }
+  if (colsum) {
+    const int c8 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) % C8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_sum[c8 * 8 + k], bsum[k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x)
+      if (s_sum[i] != 0.f) atomicAdd(colsum + i, s_sum[i]);
+  }
 }
 
-void maxpool2x2_relu_bwd(const bf16* y, const bf16* dp, bf16* dz, int N, int H, int W, int C,
-                         cudaStream_t s) {
+void maxpool2x2_relu_bwd(const bf16* y, const bf16* dp, bf16* dz, float* colsum, int N, int H, int W,
+                         int C, cudaStream_t s) {
   if (C % 8 || H % 2 || W % 2) throw std::runtime_error("[b200] maxpool2x2_bwd: need C%8==0 and even H,W");
+  if (colsum && 256 % (C / 8) != 0)
+    throw std::runtime_error("[b200] maxpool2x2_bwd: fused column sum needs C/8 to divide 256");
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
   const int blocks = min(ceil_div_ll(total, 256), 148 * 16);
-  maxpool2x2_relu_bwd_kernel<<<blocks, 256, 0, s>>>(y, dp, dz, N, H, W, C);
+  maxpool2x2_relu_bwd_kernel<<<blocks, 256, colsum ? C * sizeof(float) : 0, s>>>(y, dp, dz, colsum, N, H, W, C);
   count_launch();
   check_last("maxpool2x2_relu_bwd");
 }
@@ -213,7 +234,21 @@ __global__ void bias_grad_kernel(const bf16* __restrict__ dz, float* __restrict_
   const long long r0 = blockIdx.x * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
   if (active) {
-    for (long long r = r0 + rl; r < r1; r += RL) {
+    long long r = r0 + rl;
+    // 4 independent 16-byte loads in flight per thread
+    for (; r + 3LL * RL < r1; r += 4LL * RL) {
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) raw[u] = ld_nc_v4(dz + (r + static_cast<long long>(u) * RL) * C + col8 * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+        unpack8(raw[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v[k];
+      }
+    }
+    for (; r < r1; r += RL) {
       float v[8];
       unpack8(ld_nc_v4(dz + r * C + col8 * 8), v);
 #pragma unroll
@@ -249,7 +284,8 @@ void bias_grad(const bf16* dz, float* db, long long rows, int C, float scale, cu
   if (RL < 1) RL = 1;
   const int threads = CG * RL;
   long long nblk = (rows + RL * 16 - 1) / (RL * 16);
-  if (nblk > 148 * 8) nblk = 148 * 8;
+  const long long cap = 148LL * 8 / ((c8 + CG - 1) / CG);
+  if (nblk > cap) nblk = cap;
   if (nblk < 1) nblk = 1;
   const long long rpb = (rows + nblk - 1) / nblk;
   dim3 grid(static_cast<unsigned>((rows + rpb - 1) / rpb), (c8 + CG - 1) / CG);

@@ -24,18 +24,24 @@ void gemm_bf16(const bf16* A, long long lda, bool a_mn, const bf16* B, long long
 // 3x3 / stride 1 / pad 1 convolution, NHWC bf16, weights [Cout][3][3][Cin] bf16.
 void conv3x3_fprop(const bf16* x, const bf16* w, const float* bias, bf16* y, int N, int H, int W,
                    int Cin, int Cout, bool relu, int bn, cudaStream_t stream);
-// dx[N,H,W,Cin] = conv_transpose(dz[N,H,W,Cout], w); optional mask: zero where mask_src <= 0.
-void conv3x3_dgrad(const bf16* dz, const bf16* w, const bf16* mask_src, bf16* dx, int N, int H,
-                   int W, int Cin, int Cout, int bn, cudaStream_t stream);
+// dx[N,H,W,Cin] = conv_transpose(dz[N,H,W,Cout], w); optional mask: zero where mask_src <= 0;
+// optional colsum[Cin] += sum over pixels of dx (the previous layer's bias gradient, fused).
+void conv3x3_dgrad(const bf16* dz, const bf16* w, const bf16* mask_src, bf16* dx, float* colsum, int N,
+                   int H, int W, int Cin, int Cout, int bn, cudaStream_t stream);
 // dw[Cout][3][3][Cin] (fp32) += scale * sum_pixels dz * shifted x.
 void conv3x3_wgrad(const bf16* dz, const bf16* x, float* dw, int N, int H, int W, int Cin,
                    int Cout, float scale, int ksplit, int bn, cudaStream_t stream);
 
+// Hardware probe for unaligned / strided SWIZZLE_128B operand views (umma_probe.cu).
+void umma_shift_probe(const bf16* A, int rows, const bf16* B, float* out, int shift, int group_pitch,
+                      int use_base_offset, int mode, cudaStream_t stream);
+
 // ---- element-wise / reduction kernels (elementwise.cu) ----------------------------------------
 void maxpool2x2_fwd(const bf16* x, bf16* y, int N, int H, int W, int C, cudaStream_t s);
 // dz[N,H,W,C] = (y == pooled(y) first match && y > 0) ? dp[N,H/2,W/2,C] : 0
-void maxpool2x2_relu_bwd(const bf16* y, const bf16* dp, bf16* dz, int N, int H, int W, int C,
-                         cudaStream_t s);
+// optional colsum[C] += sum over pixels of dz (the layer's bias gradient, fused).
+void maxpool2x2_relu_bwd(const bf16* y, const bf16* dp, bf16* dz, float* colsum, int N, int H, int W,
+                         int C, cudaStream_t s);
 void adaptive_avgpool_fwd(const bf16* x, bf16* y, int N, int H, int W, int C, int OH, int OW,
                           cudaStream_t s);
 void adaptive_avgpool_bwd(const bf16* dy, bf16* dx, int N, int H, int W, int C, int OH, int OW,

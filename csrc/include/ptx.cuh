@@ -199,7 +199,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= 1ull << 46;                                            // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>((smem_addr >> 7) & 0x7) << 49;   // base offset (0 when 1 KB aligned)
+  // base offset (bits 49-51) stays 0 even for start addresses that are not 1 KB aligned: measured
+  // on B200 (bench/probe_shift.py) the swizzle XOR is taken from the absolute smem address bits,
+  // so row-shifted views of a TMA-written tile are read correctly with base_offset = 0 and are
+  // corrupted with base_offset = (addr >> 7) & 7.
   d |= 2ull << 61;                                            // SWIZZLE_128B
   return d;
 }

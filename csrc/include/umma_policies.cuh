@@ -26,6 +26,8 @@ enum GemmEpi : int {
 struct GemmParams {
   CUtensorMap mapA;
   CUtensorMap mapB;
+  int num_tiles;          // tiles_m * tiles_n * ksplit
+  int tiles_m, tiles_n;
   int M, N;               // valid output extent (rows of A-side, rows of B-side)
   int k_iters_total;      // ceil(K / 64)
   int k_iters_per_split;
@@ -42,19 +44,28 @@ struct GemmPolicy {
   static constexpr bool A_MN = A_MN_;
   static constexpr bool B_MN = B_MN_;
   using Params = GemmParams;
+  static constexpr int EPI_SMEM = 0;
+  __device__ static void epi_begin(const Params&, float*, int) {}
+  __device__ static void epi_end(const Params&, float*, int) {}
   struct Ctx {
     int m0, n0, k_begin, nk;
   };
+  struct RowCtx {};
+  __device__ static RowCtx row_ctx(const Params&, const Ctx&, int) { return RowCtx{}; }
 
   __device__ static void prefetch(const Params& p) {
     tma_prefetch_desc(&p.mapA);
     tma_prefetch_desc(&p.mapB);
   }
-  __device__ static Ctx make_ctx(const Params& p) {
+  __device__ static Ctx make_ctx(const Params& p, int tile) {
     Ctx c;
-    c.m0 = blockIdx.x * UMMA_BM;
-    c.n0 = blockIdx.y * BN;
-    c.k_begin = blockIdx.z * p.k_iters_per_split;
+    const int tm = tile % p.tiles_m;
+    const int rest = tile / p.tiles_m;
+    const int tn = rest % p.tiles_n;
+    const int tz = rest / p.tiles_n;
+    c.m0 = tm * UMMA_BM;
+    c.n0 = tn * BN;
+    c.k_begin = tz * p.k_iters_per_split;
     int rem = p.k_iters_total - c.k_begin;
     c.nk = rem < 0 ? 0 : (rem < p.k_iters_per_split ? rem : p.k_iters_per_split);
     return c;
@@ -80,8 +91,8 @@ struct GemmPolicy {
     }
   }
 
-  __device__ static void epilogue(const Params& p, const Ctx& c, int row, int col0,
-                                  const uint32_t (&acc)[32]) {
+  __device__ static void epilogue(const Params& p, const Ctx& c, const RowCtx&, int row, int col0,
+                                  const uint32_t (&acc)[32], float*) {
     const int r = c.m0 + row;
     const int cb = c.n0 + col0;
     if (r >= p.M || cb >= p.N) return;
@@ -140,17 +151,22 @@ struct ConvTile {
   int N, H, W;            // activation extent
   int Wb, Hb, Nb;         // pixel box of one tile (Wb*Hb*Nb = 128 for fprop/dgrad, 64 for wgrad)
   int tiles_w, tiles_h;   // ceil(W/Wb), ceil(H/Hb)
+  int wb_shift, hb_shift; // log2(Wb), log2(Hb): the box sides are powers of two
 };
 
 enum ConvFlags : int {
   CONV_BIAS = 1,          // add bias[channel]
   CONV_RELU = 2,          // clamp at 0
   CONV_MASK = 4,          // zero where mask_src <= 0 (ReLU backward fused into dgrad)
+  CONV_COLSUM = 8,        // colsum[channel] += sum over pixels of the stored (bf16-rounded) output:
+                          // the bias gradient of the previous layer, for free in the dgrad epilogue
 };
 
 struct ConvParams {
   CUtensorMap mapA;       // activation, dims {Ca, W, H, N}, box {64, Wb, Hb, Nb}
   CUtensorMap mapB;       // weights as 2-D [Cout][9*Cin]
+  int num_tiles;          // pixel tiles * channel tiles
+  int tiles_m;            // pixel tiles (fastest: neighbouring CTAs share halos and the weight tile in L2)
   ConvTile t;
   int Ca;                 // channels of the A activation (GEMM K per tap)
   int Cn;                 // channels of the output (GEMM N)
@@ -158,7 +174,9 @@ struct ConvParams {
   __nv_bfloat16* out;     // NHWC [N][H][W][Cn]
   const float* bias;
   const __nv_bfloat16* mask_src;
+  float* colsum;          // [Cn] fp32, accumulated with atomics (CONV_COLSUM)
   int flags;
+  int resident;           // halo kernel: all weight tiles stay in shared memory for the CTA lifetime
 };
 
 __device__ __forceinline__ void conv_tile_origin(const ConvTile& t, int tile, int& n0, int& h0,
@@ -179,17 +197,55 @@ struct ConvPolicy {
   static constexpr bool A_MN = false;
   static constexpr bool B_MN = DGRAD;
   using Params = ConvParams;
+  // epilogue scratch [512] floats: dgrad = per-CTA channel sums (fused bias gradient);
+  // fprop = the bias vector, staged once per CTA and read back as broadcast float4 loads
+  static constexpr int EPI_MAXC = 512;
+  static constexpr int EPI_SMEM = EPI_MAXC * 4;
+  __device__ static void epi_begin(const Params& p, float* sm, int tid) {
+    if constexpr (DGRAD) {
+      if (p.flags & CONV_COLSUM)
+        for (int i = tid; i < EPI_MAXC; i += 256) sm[i] = 0.f;
+    } else {
+      if (p.flags & CONV_BIAS)
+        for (int i = tid; i < p.Cn && i < EPI_MAXC; i += 256) sm[i] = p.bias[i];
+    }
+  }
+  __device__ static void epi_end(const Params& p, float* sm, int tid) {
+    if constexpr (DGRAD) {
+      if (p.flags & CONV_COLSUM)
+        for (int i = tid; i < p.Cn; i += 256) {
+          const float v = sm[i];
+          if (v != 0.f) atomicAdd(p.colsum + i, v);
+        }
+    }
+  }
   struct Ctx {
     int n0, h0, w0, c0, cchunks;
   };
+  struct RowCtx {
+    long long pix_off;      // element offset of this thread's pixel (channel 0) in the NHWC output
+    bool valid;
+  };
+  __device__ static RowCtx row_ctx(const Params& p, const Ctx& c, int row) {
+    const ConvTile& t = p.t;
+    const int ww = row & (t.Wb - 1);
+    const int r2 = row >> t.wb_shift;
+    const int hh = r2 & (t.Hb - 1);
+    const int nn = r2 >> t.hb_shift;
+    const int n = c.n0 + nn, h = c.h0 + hh, w = c.w0 + ww;
+    RowCtx rc;
+    rc.valid = n < t.N && h < t.H && w < t.W;
+    rc.pix_off = ((static_cast<long long>(n) * t.H + h) * t.W + w) * p.Cn;
+    return rc;
+  }
   __device__ static void prefetch(const Params& p) {
     tma_prefetch_desc(&p.mapA);
     tma_prefetch_desc(&p.mapB);
   }
-  __device__ static Ctx make_ctx(const Params& p) {
+  __device__ static Ctx make_ctx(const Params& p, int tile) {
     Ctx c;
-    conv_tile_origin(p.t, blockIdx.x, c.n0, c.h0, c.w0);
-    c.c0 = blockIdx.y * BN;
+    conv_tile_origin(p.t, tile % p.tiles_m, c.n0, c.h0, c.w0);
+    c.c0 = (tile / p.tiles_m) * BN;
     c.cchunks = p.Ca / UMMA_BK;
     return c;
   }
@@ -211,46 +267,75 @@ struct ConvPolicy {
     }
   }
 
-  __device__ static void epilogue(const Params& p, const Ctx& c, int row, int col0,
-                                  const uint32_t (&acc)[32]) {
-    const ConvTile& t = p.t;
-    const int ww = row % t.Wb;
-    const int r2 = row / t.Wb;
-    const int hh = r2 % t.Hb;
-    const int nn = r2 / t.Hb;
-    const int n = c.n0 + nn, h = c.h0 + hh, w = c.w0 + ww;
+  __device__ static void epilogue(const Params& p, const Ctx& c, const RowCtx& rc, int row, int col0,
+                                  const uint32_t (&acc)[32], float* sm) {
     const int ch = c.c0 + col0;
-    if (n >= t.N || h >= t.H || w >= t.W || ch >= p.Cn) return;
-    const long long off = ((static_cast<long long>(n) * t.H + h) * t.W + w) * p.Cn + ch;
+    const bool valid = rc.valid && ch < p.Cn;
+    const long long off = rc.pix_off + ch;
     __nv_bfloat16* o = p.out + off;
+    const bool colsum = DGRAD && (p.flags & CONV_COLSUM);
+    const int lane = row & 31;
+    float cs[32];                                           // what this thread stored (bf16-rounded)
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(acc[j + u]);
-      if (p.flags & CONV_BIAS) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch + j));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch + j + 4));
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-      }
-      if (p.flags & CONV_RELU) {
+      if (valid) {
+        if (!DGRAD && (p.flags & CONV_BIAS)) {
+          const float4 b0 = *reinterpret_cast<const float4*>(sm + ch + j);     // smem broadcast
+          const float4 b1 = *reinterpret_cast<const float4*>(sm + ch + j + 4);
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (p.flags & CONV_RELU) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
-      }
-      if (p.flags & CONV_MASK) {
-        const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask_src + off + j));
-        const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+          for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
+        }
+        if (p.flags & CONV_MASK) {
+          const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask_src + off + j));
+          const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float2 f = unpack_bf16x2(mw[u]);
-          if (!(f.x > 0.f)) v[2 * u] = 0.f;
-          if (!(f.y > 0.f)) v[2 * u + 1] = 0.f;
+          for (int u = 0; u < 4; ++u) {
+            const float2 f = unpack_bf16x2(mw[u]);
+            if (!(f.x > 0.f)) v[2 * u] = 0.f;
+            if (!(f.y > 0.f)) v[2 * u + 1] = 0.f;
+          }
+        }
+        const uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                    pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(o + j) = pk;
+        if (colsum) {        // sum exactly what was stored, like a separate pass over dz would
+          const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 f = unpack_bf16x2(pw[u]);
+            cs[j + 2 * u] = f.x;
+            cs[j + 2 * u + 1] = f.y;
+          }
+        }
+      } else if (colsum) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cs[j + u] = 0.f;
+      }
+    }
+    if (colsum) {
+      // Transpose-reduce across the warp with shuffles (recursive halving, 31 SHFL): afterwards
+      // lane l holds the sum over the warp's 32 pixels of column l.  No shared-memory traffic --
+      // the operand staging already saturates it.
+      __syncwarp();
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+          const float keep = upper ? cs[i + s] : cs[i];
+          const float send = upper ? cs[i] : cs[i + s];
+          cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
         }
       }
-      const uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                  pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-      *reinterpret_cast<uint4*>(o + j) = pk;
+      const int cc = c.c0 + col0 + lane;
+      if (cc < p.Cn && cc < EPI_MAXC) atomicAdd(sm + cc, cs[0]);
     }
   }
 };
@@ -259,6 +344,8 @@ struct ConvPolicy {
 struct WgradParams {
   CUtensorMap mapA;       // dZ, dims {Cout, W, H, N}, box {64, Wb, Hb, Nb} (64 pixels)
   CUtensorMap mapB;       // X,  dims {Cin,  W, H, N}, same box
+  int num_tiles;          // tiles_m * tiles_n * 9 * ksplit
+  int tiles_m, tiles_n;
   ConvTile t;
   int Cout, Cin;
   int total_tiles;        // pixel tiles = tiles_w * tiles_h * tiles_n
@@ -275,19 +362,30 @@ struct WgradPolicy {
   static constexpr bool A_MN = true;
   static constexpr bool B_MN = true;
   using Params = WgradParams;
+  static constexpr int EPI_SMEM = 0;
+  __device__ static void epi_begin(const Params&, float*, int) {}
+  __device__ static void epi_end(const Params&, float*, int) {}
   struct Ctx {
     int m0, c0, tap, tile_begin, nk;
   };
+  struct RowCtx {};
+  __device__ static RowCtx row_ctx(const Params&, const Ctx&, int) { return RowCtx{}; }
   __device__ static void prefetch(const Params& p) {
     tma_prefetch_desc(&p.mapA);
     tma_prefetch_desc(&p.mapB);
   }
-  __device__ static Ctx make_ctx(const Params& p) {
+  __device__ static Ctx make_ctx(const Params& p, int tile) {
     Ctx c;
-    c.m0 = blockIdx.x * UMMA_BM;
-    c.c0 = blockIdx.y * BN;
-    c.tap = blockIdx.z / p.ksplit;
-    const int split = blockIdx.z - c.tap * p.ksplit;
+    // tap fastest, then the channel tiles, pixel split slowest: the CTAs that run together read
+    // the SAME pixel range of dZ / X for different taps and channel tiles, so it comes from DRAM
+    // once and from L2 for everybody else (ncu: split-fastest order re-streamed both tensors from
+    // DRAM once per tap -- 89 % DRAM utilisation on features.2).
+    c.tap = tile % 9;
+    int rest = tile / 9;
+    c.m0 = (rest % p.tiles_m) * UMMA_BM;
+    rest /= p.tiles_m;
+    c.c0 = (rest % p.tiles_n) * BN;
+    const int split = rest / p.tiles_n;
     c.tile_begin = split * p.tiles_per_split;
     int rem = p.total_tiles - c.tile_begin;
     c.nk = rem < 0 ? 0 : (rem < p.tiles_per_split ? rem : p.tiles_per_split);
@@ -308,8 +406,8 @@ struct WgradPolicy {
       tma_load_4d(sB + j * UMMA_SLAB_BYTES, &p.mapB, bar, c.c0 + 64 * j, w0 + dw, h0 + dh, n0);
   }
 
-  __device__ static void epilogue(const Params& p, const Ctx& c, int row, int col0,
-                                  const uint32_t (&acc)[32]) {
+  __device__ static void epilogue(const Params& p, const Ctx& c, const RowCtx&, int row, int col0,
+                                  const uint32_t (&acc)[32], float*) {
     const int co = c.m0 + row;
     const int ci = c.c0 + col0;
     if (co >= p.Cout || ci >= p.Cin) return;

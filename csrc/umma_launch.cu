@@ -10,6 +10,7 @@
 #include <string>
 
 #include "api.h"
+#include "conv_halo.cuh"
 #include "umma_policies.cuh"
 
 namespace b200 {
@@ -74,9 +75,23 @@ static void map_nhwc(CUtensorMap* m, const bf16* p, int N, int H, int W, int C, 
   encode(m, p, 4, dims, str, box);
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// Persistent launch: one CTA per SM (or fewer when there are fewer tiles).
 template <class P>
-static void launch(const typename P::Params& prm, dim3 grid, cudaStream_t stream) {
-  constexpr int smem = umma_smem_bytes<P::BN, P::STAGES>();
+static void launch(const typename P::Params& prm, cudaStream_t stream) {
+  if (prm.num_tiles <= 0) return;
+  dim3 grid(prm.num_tiles < num_sms() ? prm.num_tiles : num_sms());
+  constexpr int smem = umma_smem_bytes<P::BN, P::STAGES>() + P::EPI_SMEM;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(umma_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -104,7 +119,50 @@ static ConvTile make_tile(int N, int H, int W, int pixels) {
   t.Nb = pixels / (t.Wb * t.Hb);
   t.tiles_w = (W + t.Wb - 1) / t.Wb;
   t.tiles_h = (H + t.Hb - 1) / t.Hb;
+  t.wb_shift = 0; while ((1 << t.wb_shift) < t.Wb) ++t.wb_shift;
+  t.hb_shift = 0; while ((1 << t.hb_shift) < t.Hb) ++t.hb_shift;
   return t;
+}
+
+// NHWC activation with an explicit pixel box {64, bw, bh, bn} (the halo kernel's (8+2) x (16+2)).
+static void map_nhwc_box(CUtensorMap* m, const bf16* p, int N, int H, int W, int C, int bw, int bh, int bn) {
+  map_nhwc(m, p, N, H, W, C, bw, bh, bn);
+}
+
+static bool halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_CONV_HALO");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+// The halo kernel tiles the image in 8 x 16 pixel blocks: use it where that wastes nothing.
+static bool halo_applicable(int H, int W) { return halo_enabled() && W % HALO_WT == 0 && H % HALO_HT == 0 && W >= 32; }
+
+template <int BN, bool DGRAD>
+static void conv_halo_launch(ConvParams& prm, const bf16* act, cudaStream_t stream) {
+  using Cfg = HaloCfg<BN>;
+  ConvTile& t = prm.t;
+  t.Wb = HALO_WT; t.Hb = HALO_HT; t.Nb = 1; t.wb_shift = 3; t.hb_shift = 4;
+  t.tiles_w = t.W / HALO_WT; t.tiles_h = t.H / HALO_HT;
+  prm.tiles_m = t.tiles_w * t.tiles_h * t.N;
+  const int tiles_n = (prm.Cn + BN - 1) / BN;
+  prm.num_tiles = prm.tiles_m * tiles_n;
+  prm.resident = (tiles_n == 1 && 9 * (prm.Ca / UMMA_BK) <= Cfg::NB) ? 1 : 0;
+  map_nhwc_box(&prm.mapA, act, t.N, t.H, t.W, prm.Ca, HALO_PITCH, HALO_HT + 2, 1);
+  constexpr int smem = Cfg::SMEM + ConvPolicy<BN, 1, DGRAD>::EPI_SMEM;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess)
+      throw std::runtime_error(std::string("[b200] cudaFuncSetAttribute(halo): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid(prm.num_tiles < num_sms() ? prm.num_tiles : num_sms());
+  conv_halo_kernel<BN, DGRAD><<<grid, UMMA_THREADS, smem, stream>>>(prm);
+  count_launch();
+  check_last("conv_halo_kernel launch");
 }
 
 // ---------------------------------------------------------------------------------------- GEMM
@@ -115,8 +173,10 @@ static void gemm_launch(GemmParams& prm, const bf16* A, long long lda, const bf1
   using P = GemmPolicy<BN, STAGES, A_MN, B_MN, EPI>;
   if (A_MN) map_2d(&prm.mapA, A, K, M, lda, 64, 64); else map_2d(&prm.mapA, A, M, K, lda, 64, UMMA_BM);
   if (B_MN) map_2d(&prm.mapB, B, K, N, ldb, 64, 64); else map_2d(&prm.mapB, B, N, K, ldb, 64, BN);
-  dim3 grid((M + UMMA_BM - 1) / UMMA_BM, (N + BN - 1) / BN, ksplit);
-  launch<P>(prm, grid, stream);
+  prm.tiles_m = (M + UMMA_BM - 1) / UMMA_BM;
+  prm.tiles_n = (N + BN - 1) / BN;
+  prm.num_tiles = prm.tiles_m * prm.tiles_n * ksplit;
+  launch<P>(prm, stream);
 }
 
 #define GEMM_BN_SWITCH(AMN, BMN, EPI)                                                       \
@@ -169,8 +229,9 @@ static void conv_launch(ConvParams& prm, cudaStream_t stream) {
   using P = ConvPolicy<BN, STAGES, DGRAD>;
   const ConvTile& t = prm.t;
   const int tiles_n = (t.N + t.Nb - 1) / t.Nb;
-  dim3 grid(t.tiles_w * t.tiles_h * tiles_n, (prm.Cn + BN - 1) / BN, 1);
-  launch<P>(prm, grid, stream);
+  prm.tiles_m = t.tiles_w * t.tiles_h * tiles_n;
+  prm.num_tiles = prm.tiles_m * ((prm.Cn + BN - 1) / BN);
+  launch<P>(prm, stream);
 }
 
 static int auto_bn(int cn, int bn) {
@@ -185,11 +246,20 @@ void conv3x3_fprop(const bf16* x, const bf16* w, const float* bias, bf16* y, int
   ConvParams prm;
   prm.t = make_tile(N, H, W, UMMA_BM);
   prm.Ca = Cin; prm.Cn = Cout; prm.wcols_per_tap = Cin;
-  prm.out = y; prm.bias = bias; prm.mask_src = nullptr;
+  prm.out = y; prm.bias = bias; prm.mask_src = nullptr; prm.colsum = nullptr;
   prm.flags = (bias ? CONV_BIAS : 0) | (relu ? CONV_RELU : 0);
   bn = auto_bn(Cout, bn);
-  map_nhwc(&prm.mapA, x, N, H, W, Cin, prm.t.Wb, prm.t.Hb, prm.t.Nb);
+  prm.resident = 0;
   map_2d(&prm.mapB, w, Cout, 9LL * Cin, 9LL * Cin, 64, bn);
+  if (halo_applicable(H, W)) {
+    switch (bn) {
+      case 64: conv_halo_launch<64, false>(prm, x, stream); return;
+      case 128: conv_halo_launch<128, false>(prm, x, stream); return;
+      case 256: conv_halo_launch<256, false>(prm, x, stream); return;
+      default: throw std::runtime_error("[b200] conv3x3_fprop: bn must be 64/128/256");
+    }
+  }
+  map_nhwc(&prm.mapA, x, N, H, W, Cin, prm.t.Wb, prm.t.Hb, prm.t.Nb);
   switch (bn) {
     case 64: conv_launch<64, false>(prm, stream); break;
     case 128: conv_launch<128, false>(prm, stream); break;
@@ -198,18 +268,28 @@ void conv3x3_fprop(const bf16* x, const bf16* w, const float* bias, bf16* y, int
   }
 }
 
-void conv3x3_dgrad(const bf16* dz, const bf16* w, const bf16* mask_src, bf16* dx, int N, int H,
-                   int W, int Cin, int Cout, int bn, cudaStream_t stream) {
+void conv3x3_dgrad(const bf16* dz, const bf16* w, const bf16* mask_src, bf16* dx, float* colsum, int N,
+                   int H, int W, int Cin, int Cout, int bn, cudaStream_t stream) {
   check_channels(Cin, "conv3x3_dgrad Cin");
   check_channels(Cout, "conv3x3_dgrad Cout");
   ConvParams prm;
   prm.t = make_tile(N, H, W, UMMA_BM);
   prm.Ca = Cout; prm.Cn = Cin; prm.wcols_per_tap = Cin;
-  prm.out = dx; prm.bias = nullptr; prm.mask_src = mask_src;
-  prm.flags = mask_src ? CONV_MASK : 0;
+  prm.out = dx; prm.bias = nullptr; prm.mask_src = mask_src; prm.colsum = colsum;
+  prm.flags = (mask_src ? CONV_MASK : 0) | (colsum ? CONV_COLSUM : 0);
+  if (colsum && Cin > 512) throw std::runtime_error("[b200] conv3x3_dgrad: fused column sum supports Cin <= 512");
   bn = auto_bn(Cin, bn);
-  map_nhwc(&prm.mapA, dz, N, H, W, Cout, prm.t.Wb, prm.t.Hb, prm.t.Nb);
+  prm.resident = 0;
   map_2d(&prm.mapB, w, Cout, 9LL * Cin, 9LL * Cin, 64, 64);   // MN-major: 64 ci x 64 co boxes
+  if (halo_applicable(H, W)) {
+    switch (bn) {
+      case 64: conv_halo_launch<64, true>(prm, dz, stream); return;
+      case 128: conv_halo_launch<128, true>(prm, dz, stream); return;
+      case 256: conv_halo_launch<256, true>(prm, dz, stream); return;
+      default: throw std::runtime_error("[b200] conv3x3_dgrad: bn must be 64/128/256");
+    }
+  }
+  map_nhwc(&prm.mapA, dz, N, H, W, Cout, prm.t.Wb, prm.t.Hb, prm.t.Nb);
   switch (bn) {
     case 64: conv_launch<64, true>(prm, stream); break;
     case 128: conv_launch<128, true>(prm, stream); break;
@@ -222,8 +302,10 @@ template <int BN>
 static void wgrad_launch(WgradParams& prm, cudaStream_t stream) {
   constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
   using P = WgradPolicy<BN, STAGES>;
-  dim3 grid((prm.Cout + UMMA_BM - 1) / UMMA_BM, (prm.Cin + BN - 1) / BN, 9 * prm.ksplit);
-  launch<P>(prm, grid, stream);
+  prm.tiles_m = (prm.Cout + UMMA_BM - 1) / UMMA_BM;
+  prm.tiles_n = (prm.Cin + BN - 1) / BN;
+  prm.num_tiles = prm.tiles_m * prm.tiles_n * 9 * prm.ksplit;
+  launch<P>(prm, stream);
 }
 
 void conv3x3_wgrad(const bf16* dz, const bf16* x, float* dw, int N, int H, int W, int Cin,
@@ -236,10 +318,11 @@ void conv3x3_wgrad(const bf16* dz, const bf16* x, float* dw, int N, int H, int W
   prm.Cout = Cout; prm.Cin = Cin;
   prm.total_tiles = prm.t.tiles_w * prm.t.tiles_h * tiles_n;
   bn = auto_bn(Cin, bn);
-  if (ksplit <= 0) {     // fill ~2 waves of 148 SMs
+  if (ksplit <= 0) {     // work items of <= ~64 k-blocks (4096 pixels), and at least ~4 per SM
     const int base = ((Cout + UMMA_BM - 1) / UMMA_BM) * ((Cin + bn - 1) / bn) * 9;
-    ksplit = (2 * 148 + base - 1) / base;
-    if (ksplit < 1) ksplit = 1;
+    ksplit = (prm.total_tiles + 63) / 64;
+    const int min_split = (4 * num_sms() + base - 1) / base;
+    if (ksplit < min_split) ksplit = min_split;
   }
   if (ksplit > prm.total_tiles) ksplit = prm.total_tiles;
   prm.tiles_per_split = (prm.total_tiles + ksplit - 1) / ksplit;

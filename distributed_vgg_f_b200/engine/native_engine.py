@@ -251,8 +251,13 @@ class NativeEngine:
             if batch.state is not None:
                 batch.state["event"] = h2d          # the loader may refill the pinned slot after this
             cur.wait_event(h2d)
-            ops.augment(self._src_u8[j][:b], self._params_dev[j][:b], self.col0[:b * HW * HW],
-                        batch.resized_hw, out_hw=HW, mode="im2col", pad=L.CONV0_K)
+            # two passes: transform once per pixel into 8-byte NHWC4 pixels (25 MB at B=64, L2
+            # resident), then expand to the first conv's im2col rows with coalesced 16-byte stores
+            if self.x_nhwc is None:
+                self.x_nhwc = torch.empty(self.B, HW, HW, 4, dtype=BF16, device=self.device)
+            ops.augment(self._src_u8[j][:b], self._params_dev[j][:b], self.x_nhwc[:b], batch.resized_hw,
+                        out_hw=HW, mode="nhwc", pad=4)
+            C.im2col_c3(self.x_nhwc[:b], self.col0[:b * HW * HW], L.CONV0_K)
             return b
         x, y = batch
         b = int(y.shape[0])
@@ -361,17 +366,21 @@ class NativeEngine:
         # invariant at loop entry: if layer i pools, `g` is dP_i (grad wrt pooled output);
         # otherwise `g` is dZ_i (grad wrt the pre-ReLU output, mask already applied).
         pp = 0
+        bias_fused = False      # was this layer's bias gradient already produced by the kernel that made dz?
         for i in range(len(convs) - 1, -1, -1):
             c = convs[i]
             y = self.acts[i][:b]
             if c.pool_after:
                 dz = self.dbuf[pp][:y.numel()].view_as(y)
-                ops.maxpool2x2_relu_bwd(y, g, out=dz)
+                # ReLU + pool backward, bias gradient (column sum of dz) fused
+                ops.maxpool2x2_relu_bwd(y, g, out=dz, colsum=self._grad(c.name + ".bias"))
                 pp ^= 1
+                bias_fused = True
             else:
                 dz = g
             M = y.numel() // c.cout
-            ops.bias_grad(dz.view(M, c.cout), self._grad(c.name + ".bias"), M, c.cout)
+            if not bias_fused:
+                ops.bias_grad(dz.view(M, c.cout), self._grad(c.name + ".bias"), M, c.cout)
             self._bucket_done(c.name + ".bias")
             if i == 0:
                 ks = max(1, min(M // 64, 296))
@@ -379,11 +388,16 @@ class NativeEngine:
                          N=L.CONV0_K, K=M, a_mn=True, b_mn=True, epi="f32_atomic", ksplit=ks, ldo=L.CONV0_K)
                 self._bucket_done(c.name + ".weight")
                 break
-            x_in = self.pools[i - 1][:b] if convs[i - 1].pool_after else self.acts[i - 1][:b]
+            prev = convs[i - 1]
+            x_in = self.pools[i - 1][:b] if prev.pool_after else self.acts[i - 1][:b]
             C.conv_wgrad(dz, x_in, self._grad(c.name + ".weight"), 1.0, 0, 0)
             dx = self.dbuf[pp][:x_in.numel()].view_as(x_in)
-            # ReLU backward of layer i-1 is fused here unless a pool sits in between
-            C.conv_dgrad(dz, self._w(c.name), None if convs[i - 1].pool_after else x_in, dx, 0)
+            # ReLU backward of layer i-1 is fused here unless a pool sits in between; when it is,
+            # dx IS dZ_{i-1} and its column sum (layer i-1's bias gradient) comes for free
+            fuse = not prev.pool_after
+            C.conv_dgrad(dz, self._w(c.name), x_in if fuse else None, dx,
+                         self._grad(prev.name + ".bias") if fuse else None, 0)
+            bias_fused = fuse
             self._bucket_done(c.name + ".weight")      # after dgrad: it reads the pre-update weights
             pp ^= 1
             g = dx

@@ -64,10 +64,11 @@ def conv3x3_fprop(x, w, bias, relu: bool = True, bn: int = 0, out=None):
     return y
 
 
-def conv3x3_dgrad(dz, w, cin: int, mask_src=None, bn: int = 0, out=None):
+def conv3x3_dgrad(dz, w, cin: int, mask_src=None, bn: int = 0, out=None, colsum=None):
+    """dx = conv_transpose(dz, w) [* (mask_src > 0)]; colsum (fp32 [cin]) += dx.sum(pixels)."""
     N, H, W, _ = dz.shape
     dx = out if out is not None else torch.empty(N, H, W, cin, dtype=torch.bfloat16, device=dz.device)
-    require().conv_dgrad(dz, w, mask_src, dx, bn)
+    require().conv_dgrad(dz, w, mask_src, dx, colsum, bn)
     return dx
 
 
@@ -85,9 +86,9 @@ def maxpool2x2(x, out=None):
     return y
 
 
-def maxpool2x2_relu_bwd(y, dp, out=None):
+def maxpool2x2_relu_bwd(y, dp, out=None, colsum=None):
     dz = out if out is not None else torch.empty_like(y)
-    require().maxpool_relu_bwd(y, dp, dz)
+    require().maxpool_relu_bwd(y, dp, dz, colsum)
     return dz
 
 

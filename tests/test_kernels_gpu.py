@@ -104,7 +104,10 @@ def _conv_ref(x, w, b):
 
 
 CONV_SHAPES = [(2, 16, 16, 64, 64), (1, 28, 28, 128, 256), (4, 14, 14, 512, 512), (2, 56, 56, 64, 128),
-               (3, 12, 20, 64, 64), (1, 224, 224, 64, 64)]
+               (3, 12, 20, 64, 64), (1, 224, 224, 64, 64),
+               # halo-tile kernel (H % 16 == 0, W % 8 == 0, W >= 32): resident / streaming weights
+               (2, 32, 32, 64, 64), (1, 32, 32, 64, 128), (1, 48, 64, 128, 128), (1, 32, 32, 256, 256),
+               (3, 16, 40, 128, 64)]
 
 
 @pytest.mark.parametrize("N,H,W,Cin,Cout", CONV_SHAPES)
@@ -129,6 +132,11 @@ def test_conv_dgrad(N, H, W, Cin, Cout):
     mask_src = bf(torch.randn(N, H, W, Cin, device=DEV))
     dx2 = ops.conv3x3_dgrad(dz, w, Cin, mask_src=mask_src)
     assert rel_err(dx2, ref * (mask_src.float() > 0)) < 1e-2
+    # fused column sum (= bias gradient of the previous layer): sums exactly what was stored
+    cs = torch.zeros(Cin, device=DEV)
+    dx3 = ops.conv3x3_dgrad(dz, w, Cin, mask_src=mask_src, colsum=cs)
+    assert torch.equal(dx3, dx2)
+    assert rel_err(cs, dx2.float().sum((0, 1, 2))) < 1e-3
 
 
 @pytest.mark.parametrize("N,H,W,Cin,Cout", CONV_SHAPES)
@@ -159,6 +167,11 @@ def test_maxpool_fwd_bwd():
     yr.backward(dp.float().permute(0, 3, 1, 2))
     ref = (xr.grad * (xr > 0)).permute(0, 2, 3, 1)
     assert rel_err(dz, ref) < 1e-6
+    # fused bias gradient (column sum of dz)
+    cs = torch.zeros(64, device=DEV)
+    dz2 = ops.maxpool2x2_relu_bwd(x, dp, colsum=cs)
+    assert torch.equal(dz2, dz)
+    assert rel_err(cs, dz.float().sum((0, 1, 2))) < 1e-4
 
 
 @pytest.mark.parametrize("H", [4, 7, 14])
