@@ -1,0 +1,120 @@
+"""Distributed plumbing without a GPU (BASELINE config #1 / SURVEY section 4): world_size=2 over
+gloo on 127.0.0.1, driven through the reference-compatible CLI and through the Python API."""
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _launch(rank, port, root, extra):
+    cmd = [sys.executable, "-m", "distributed_vgg_f_b200", "-iu", "tcp://127.0.0.1:%d" % port, "-rn", str(rank),
+           "-ws", "2", "-rd", root, "-ep", "2", "-nc", "-lr", "0.001", "-mb", "4", "--model", "vggf-tiny",
+           "--engine", "oracle"] + extra
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="2")
+    return subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+
+
+def test_cli_two_ranks_gloo(synth_root, tmp_path):
+    port = _free_port()
+    ck = str(tmp_path / "ck.pt")
+    procs = [_launch(r, port, synth_root, ["--save", ck]) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    pat = re.compile(r"\[Info\] Epoch: (\d)/2, train loss: ([\d.]+), train acc: ([\d.]+)%, "
+                     r"test loss: ([\d.]+), test acc: ([\d.]+)%\.")
+    per_rank = []
+    for r, out in enumerate(outs):
+        assert out.startswith("Namespace("), out[:200]                       # distributedVggf.py:281
+        assert "[Info] number of classes: 3" in out
+        assert "[Info] class labels: ['edible', 'other', 'toy']" in out
+        assert "[Info] Running instance %d using cpu" % r in out
+        assert "[Info] distributed training has been initialized" in out
+        lines = pat.findall(out)
+        assert len(lines) == 2, out
+        per_rank.append(lines)
+    # validation is unsharded and the replicas are synchronised: identical test loss on both ranks,
+    # while the (sharded) train loss differs -- exactly what the reference shows
+    for e in range(2):
+        assert per_rank[0][e][3] == per_rank[1][e][3] and per_rank[0][e][4] == per_rank[1][e][4]
+    assert per_rank[0][0][1] != per_rank[1][0][1]
+    payload = torch.load(ck, weights_only=False)                             # rank 0 wrote it
+    assert payload["epoch"] == 2 and all(k.startswith("module.") for k in payload["model"])
+
+
+def _ddp_worker(rank, world, port, root):
+    import torch.distributed as dist
+
+    from distributed_vgg_f_b200.data.loader import DataManager
+    from distributed_vgg_f_b200.models.vggf import build_oracle, vggf_tiny_spec
+    from distributed_vgg_f_b200.parallel.ddp import FlatDDP
+    from distributed_vgg_f_b200.trainer import Trainer
+
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    model = build_oracle(vggf_tiny_spec(3), seed=rank)          # different init per rank on purpose
+    ddp = FlatDDP(model, bucket_cap_mb=0.05)                    # many small buckets
+    assert len(ddp.plan.buckets) > 3
+    flat0 = torch.cat([p.detach().flatten() for p in model.parameters()])
+    ref = flat0.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(flat0, ref), "constructor did not broadcast rank 0's parameters"
+    opt = torch.optim.Adam(ddp.parameters(), lr=1e-3)
+    tr = DataManager(root, 4, train=True, world_size=world, rank=rank).get_loader()
+    va = DataManager(root, 4, train=False, world_size=world, rank=rank).get_loader()
+    Trainer(ddp, opt, tr, va, torch.device("cpu"), verbose_throughput=False).fit(1)
+    flat = torch.cat([p.detach().flatten() for p in model.parameters()])
+    ref = flat.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(flat, ref), "replicas diverged"
+    assert not torch.equal(flat, flat0)
+    dist.destroy_process_group()
+
+
+def test_flat_ddp_keeps_replicas_identical(synth_root):
+    import torch.multiprocessing as mp
+
+    mp.spawn(_ddp_worker, args=(2, _free_port(), synth_root), nprocs=2, join=True)
+
+
+def test_flat_ddp_matches_single_process_gradients():
+    """Average of two half-batch gradients == full-batch gradient (bucketed all-reduce, 1/ws)."""
+    import torch.multiprocessing as mp
+
+    mp.spawn(_grad_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def _grad_worker(rank, world, port):
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    from distributed_vgg_f_b200.models.vggf import build_oracle, vggf_tiny_spec
+    from distributed_vgg_f_b200.parallel.ddp import FlatDDP
+
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(4, 3, 64, 64, generator=g)
+    y = torch.randint(0, 3, (4,), generator=g)
+    single = build_oracle(vggf_tiny_spec(3), seed=0).eval()
+    F.cross_entropy(single(x), y).backward()
+    ddp = FlatDDP(build_oracle(vggf_tiny_spec(3), seed=0).eval(), bucket_cap_mb=0.05)
+    ddp.zero_grad()
+    F.cross_entropy(ddp(x[2 * rank:2 * rank + 2]), y[2 * rank:2 * rank + 2]).backward()
+    ddp.finish_backward()
+    for (n, a), (_, b) in zip(ddp.module.named_parameters(), single.named_parameters()):
+        assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-6), n
+    dist.destroy_process_group()
