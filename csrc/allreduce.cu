@@ -100,17 +100,34 @@ __global__ void __launch_bounds__(AR_THREADS, 1) allreduce_kernel(const ArArgs a
   uint8_t* my_wire = reinterpret_cast<uint8_t*>(c.wire_ptrs[rank]) + a.start * (WIRE32 ? 4 : 2);
 
   // ---- pack: fp32 arena -> wire (scaled, rounded once) -----------------------------------------
+  constexpr int UNR = 4;        // independent 16-byte transactions in flight per thread
   if (a.grad) {
     const float* g = a.grad + a.start;
-    for (long long v = chunk0 + threadIdx.x; v < chunk1; v += AR_THREADS) {
+    const float s = a.inv_world;
+    long long v = chunk0 + threadIdx.x;
+    if constexpr (!WIRE32) {
+      for (; v + (UNR - 1) * AR_THREADS < chunk1; v += UNR * AR_THREADS) {
+        float4 x0[UNR], x1[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          x0[u] = *reinterpret_cast<const float4*>(g + (v + u * AR_THREADS) * 8);
+          x1[u] = *reinterpret_cast<const float4*>(g + (v + u * AR_THREADS) * 8 + 4);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+          st_v4(my_wire + (v + u * AR_THREADS) * 16,
+                make_uint4(pack_bf16x2(x0[u].x * s, x0[u].y * s), pack_bf16x2(x0[u].z * s, x0[u].w * s),
+                           pack_bf16x2(x1[u].x * s, x1[u].y * s), pack_bf16x2(x1[u].z * s, x1[u].w * s)));
+      }
+    }
+    for (; v < chunk1; v += AR_THREADS) {
       if constexpr (WIRE32) {
         float4 x = *reinterpret_cast<const float4*>(g + v * 4);
-        x.x *= a.inv_world; x.y *= a.inv_world; x.z *= a.inv_world; x.w *= a.inv_world;
+        x.x *= s; x.y *= s; x.z *= s; x.w *= s;
         *reinterpret_cast<float4*>(my_wire + v * 16) = x;
       } else {
         const float4 x0 = *reinterpret_cast<const float4*>(g + v * 8);
         const float4 x1 = *reinterpret_cast<const float4*>(g + v * 8 + 4);
-        const float s = a.inv_world;
         st_v4(my_wire + v * 16, make_uint4(pack_bf16x2(x0.x * s, x0.y * s), pack_bf16x2(x0.z * s, x0.w * s),
                                            pack_bf16x2(x1.x * s, x1.y * s), pack_bf16x2(x1.z * s, x1.w * s)));
       }
@@ -175,7 +192,17 @@ __global__ void __launch_bounds__(AR_THREADS, 1) allreduce_kernel(const ArArgs a
     }
   } else {   // AR_NVLS: the switch reduces and broadcasts
     uint8_t* mc = reinterpret_cast<uint8_t*>(c.wire_mc) + a.start * (WIRE32 ? 4 : 2);
-    for (long long v = cell0 + threadIdx.x; v < cell1; v += AR_THREADS) {
+    long long v = cell0 + threadIdx.x;
+    if constexpr (!WIRE32) {
+      for (; v + (UNR - 1) * AR_THREADS < cell1; v += UNR * AR_THREADS) {
+        uint4 r[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) r[u] = multimem_ld_reduce_bf16x8(mc + (v + u * AR_THREADS) * 16);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) multimem_st_v4(mc + (v + u * AR_THREADS) * 16, r[u]);
+      }
+    }
+    for (; v < cell1; v += AR_THREADS) {
       if constexpr (WIRE32) {
         const float4 r = multimem_ld_reduce_f32x4(mc + v * 16);
         multimem_st_v4(mc + v * 16, make_uint4(__float_as_uint(r.x), __float_as_uint(r.y),
@@ -190,7 +217,23 @@ __global__ void __launch_bounds__(AR_THREADS, 1) allreduce_kernel(const ArArgs a
   // ---- unpack (optional): wire -> fp32 arena ----------------------------------------------------
   if (a.grad_out) {
     float* out = a.grad_out + a.start;
-    for (long long v = chunk0 + threadIdx.x; v < chunk1; v += AR_THREADS) {
+    long long v = chunk0 + threadIdx.x;
+    if constexpr (!WIRE32) {
+      for (; v + (UNR - 1) * AR_THREADS < chunk1; v += UNR * AR_THREADS) {
+        uint4 raw[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) raw[u] = ld_v4(my_wire + (v + u * AR_THREADS) * 16);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const float2 f0 = unpack_bf16x2(raw[u].x), f1 = unpack_bf16x2(raw[u].y), f2 = unpack_bf16x2(raw[u].z),
+                       f3 = unpack_bf16x2(raw[u].w);
+          float* o = out + (v + u * AR_THREADS) * 8;
+          *reinterpret_cast<float4*>(o) = make_float4(f0.x, f0.y, f1.x, f1.y);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+        }
+      }
+    }
+    for (; v < chunk1; v += AR_THREADS) {
       const uint4 raw = ld_v4(my_wire + v * 16);
       if constexpr (WIRE32) {
         *reinterpret_cast<uint4*>(out + v * 4) = raw;

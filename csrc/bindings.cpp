@@ -220,6 +220,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.attr("EPI_F32_ATOMIC_T") = 2;
   m.attr("EPI_BF16_BIAS_RELU") = 3;
   m.attr("EPI_F32_STORE_T") = 4;
+  m.attr("EPI_BF16_STORE") = 5;
   m.attr("AR_ONESHOT") = 0;
   m.attr("AR_TWOSHOT") = 1;
   m.attr("AR_NVLS") = 2;

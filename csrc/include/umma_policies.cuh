@@ -21,6 +21,7 @@ enum GemmEpi : int {
   EPI_F32_ATOMIC_T = 2,   // out[col*ldo + row] += acc                     (swap-AB FC, split-K)
   EPI_BF16_BIAS_RELU = 3, // out[row*ldo + col] = bf16(relu(acc + bias[col]))
   EPI_F32_STORE_T = 4,    // out[col*ldo + row] = acc
+  EPI_BF16_STORE = 5,     // out[row*ldo + col] = bf16(alpha * acc)   (FC wgrad straight into the bf16 wire)
 };
 
 struct GemmParams {
@@ -127,6 +128,21 @@ struct GemmPolicy {
           if constexpr (EPI == EPI_F32_ATOMIC_T) atomicAdd(o + static_cast<long long>(j) * p.ldo, __uint_as_float(acc[j]) * alpha);
           else o[static_cast<long long>(j) * p.ldo] = __uint_as_float(acc[j]) * alpha;
         }
+      }
+    } else if constexpr (EPI == EPI_BF16_STORE) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(r) * p.ldo + cb;
+      if ((cb + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const uint4 pk = make_uint4(
+              pack_bf16x2(__uint_as_float(acc[j]) * alpha, __uint_as_float(acc[j + 1]) * alpha),
+              pack_bf16x2(__uint_as_float(acc[j + 2]) * alpha, __uint_as_float(acc[j + 3]) * alpha),
+              pack_bf16x2(__uint_as_float(acc[j + 4]) * alpha, __uint_as_float(acc[j + 5]) * alpha),
+              pack_bf16x2(__uint_as_float(acc[j + 6]) * alpha, __uint_as_float(acc[j + 7]) * alpha));
+          *reinterpret_cast<uint4*>(o + j) = pk;
+        }
+      } else {
+        for (int j = 0; j < 32 && cb + j < p.N; ++j) o[j] = __float2bfloat16(__uint_as_float(acc[j]) * alpha);
       }
     } else if constexpr (EPI == EPI_BF16_BIAS_RELU) {
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(r) * p.ldo + cb;

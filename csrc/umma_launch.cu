@@ -214,6 +214,7 @@ void gemm_bf16(const bf16* A, long long lda, bool a_mn, const bf16* B, long long
   } else if (a_mn && b_mn) {
     if (epi == EPI_F32_STORE) { GEMM_BN_SWITCH(true, true, EPI_F32_STORE) }
     if (epi == EPI_F32_ATOMIC) { GEMM_BN_SWITCH(true, true, EPI_F32_ATOMIC) }
+    if (epi == EPI_BF16_STORE) { GEMM_BN_SWITCH(true, true, EPI_BF16_STORE) }
   }
   throw std::runtime_error("[b200] gemm_bf16: unsupported (layout, epilogue, bn) combination");
 }

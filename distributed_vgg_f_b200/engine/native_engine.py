@@ -131,6 +131,17 @@ class NativeEngine:
             self.arena = SymmetricArena(n, dev, wire_dtype=wdt)
         if self.world > 1:
             self._broadcast_params()
+        # FC weights that span whole buckets by themselves can be produced directly as bf16 on the wire
+        self._prepacked = set()
+        self._bucket_prepacked = [False] * len(self.plan.buckets)
+        if self.arena is not None and self.arena.wire_dtype == BF16:
+            for f in spec.fcs:
+                name = f.name + ".weight"
+                ids = self.plan.bucket_of(name)
+                if ids and all(self.plan.buckets[i].tensors == (name,) for i in ids):
+                    self._prepacked.add(name)
+                    for i in ids:
+                        self._bucket_prepacked[i] = True
 
         self._build_buffers()
 
@@ -340,8 +351,16 @@ class NativeEngine:
             ops.bias_grad(dz, self._grad(f.name + ".bias"), b, f.fout, ld=ld)
             self._bucket_done(f.name + ".bias")
             # wgrad: dW[fout][fin] = dz^T x_in   (both operands MN-major: stored [K=b][*])
-            ops.gemm(dz, x_in, self._grad(f.name + ".weight"), M=f.fout, N=f.fin, K=b, a_mn=True, b_mn=True,
-                     epi="f32_store", ldo=f.fin)
+            if (f.name + ".weight") in self._prepacked:
+                # big FC weights own whole buckets: write bf16(dW / ws) straight into the symmetric
+                # wire buffer -- no fp32 gradient, no pack pass before the reduction
+                off = self.plan.offsets[f.name + ".weight"]
+                wire_w = self.arena.wire[off:off + f.fout * f.fin].view(f.fout, f.fin)
+                ops.gemm(dz, x_in, wire_w, M=f.fout, N=f.fin, K=b, a_mn=True, b_mn=True, epi="bf16_store",
+                         ldo=f.fin, alpha=1.0 / self.world)
+            else:
+                ops.gemm(dz, x_in, self._grad(f.name + ".weight"), M=f.fout, N=f.fin, K=b, a_mn=True,
+                         b_mn=True, epi="f32_store", ldo=f.fin)
             # dgrad: dX[b][fin] = dz W ; swap-AB with W read MN-major (stored [K=fout][M=fin])
             m_tiles = (f.fin + 127) // 128
             ks = self._ksplit(m_tiles, (f.fout + 63) // 64)
@@ -415,16 +434,17 @@ class NativeEngine:
             if self._missing[bi] == 0:
                 self._reduce_and_update(bi)
 
-    def _apply_update(self, s: int, e: int, g16: Optional[torch.Tensor]) -> None:
+    def _apply_update(self, s: int, e: int, g16: Optional[torch.Tensor], zero: bool = True) -> None:
         g32 = None if g16 is not None else self.g32[s:e]
+        z = self.g32[s:e] if zero else None      # ranges written with plain stores need no re-zeroing
         if self.opt_name == "adam":
             ops.adam_step(self.p32[s:e], self.m32[s:e], self.v32[s:e], g32=g32, g16=g16, shadow=self.w16[s:e],
                           lr=self.lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps,
-                          weight_decay=self.weight_decay, step=self.step_count, zero=self.g32[s:e])
+                          weight_decay=self.weight_decay, step=self.step_count, zero=z)
         else:
             ops.sgd_step(self.p32[s:e], self.m32[s:e], g32=g32, g16=g16, shadow=self.w16[s:e], lr=self.lr,
                          momentum=self.momentum, weight_decay=self.weight_decay,
-                         first=(self.step_count == 1), zero=self.g32[s:e])
+                         first=(self.step_count == 1), zero=z)
 
     def _reduce_and_update(self, bi: int) -> None:
         bk = self.plan.buckets[bi]
@@ -444,12 +464,15 @@ class NativeEngine:
                     self._apply_update(s, e, None)
                 return
             algo = self.arena.pick_algo(e - s, self.ar_algo)
+            prepacked = self._bucket_prepacked[bi]
+            if prepacked and algo == "oneshot":
+                algo = "twoshot"                 # one-shot cannot leave its result on the wire
             to_f32 = (algo == "oneshot" or self.unpack_fp32 or self.arena.wire_dtype == F32
                       or not self.apply_updates)
-            self.arena.allreduce(self.g32, self.g32 if to_f32 else None, s, e - s, algo=algo,
-                                 slot=bi % self.arena.slots, max_ctas=self.comm_ctas)
+            self.arena.allreduce(None if prepacked else self.g32, self.g32 if to_f32 else None, s, e - s,
+                                 algo=algo, slot=bi % self.arena.slots, max_ctas=self.comm_ctas)
             if self.apply_updates:
-                self._apply_update(s, e, None if to_f32 else self.arena.wire[s:e])
+                self._apply_update(s, e, None if to_f32 else self.arena.wire[s:e], zero=not prepacked)
 
     def _end_step(self) -> None:
         if self.world > 1:

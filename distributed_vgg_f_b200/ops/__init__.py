@@ -51,7 +51,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     C = require()
     code = {"f32_store": C.EPI_F32_STORE, "f32_atomic": C.EPI_F32_ATOMIC,
             "f32_atomic_t": C.EPI_F32_ATOMIC_T, "bf16_bias_relu": C.EPI_BF16_BIAS_RELU,
-            "f32_store_t": C.EPI_F32_STORE_T}[epi]
+            "f32_store_t": C.EPI_F32_STORE_T, "bf16_store": C.EPI_BF16_STORE}[epi]
     if ldo is None:
         ldo = out.stride(0)
     C.gemm(a, a_mn, b, b_mn, M, N, K, out, ldo, code, bias, alpha, ksplit, bn)
