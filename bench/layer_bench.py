@@ -72,6 +72,9 @@ for i, c in enumerate(spec.convs):
         for bn in ([64] if c.cin == 64 else [128, 256] if c.cin >= 256 else [128]):
             t = timeit(lambda: C.conv_wgrad(dz, x, dw, 1.0, 0, bn))
             rows.append(("%s wgrad bn%d" % (c.name, bn), t, fl, 0))
+        if c.cin == 64:
+            t = timeit(lambda: C.conv_wgrad(dz, x, dw, 1.0, 0, 0))
+            rows.append(("%s wgrad halo64" % c.name, t, fl, 0))
         if with_torch:
             xt = x.permute(0, 3, 1, 2)            # NCHW view, channels_last memory
             wt = w.permute(0, 3, 1, 2)

@@ -11,6 +11,7 @@
 
 #include "api.h"
 #include "conv_halo.cuh"
+#include "wgrad_halo.cuh"
 #include "umma_policies.cuh"
 
 namespace b200 {
@@ -309,10 +310,43 @@ static void wgrad_launch(WgradParams& prm, cudaStream_t stream) {
   launch<P>(prm, stream);
 }
 
+// 64-input-channel layers on 8-divisible maps: nine tap views of one X halo per pixel tile.
+static void wgrad_halo64_launch(const bf16* dz, const bf16* x, float* dw, int N, int H, int W, int Cout,
+                                float scale, cudaStream_t stream) {
+  WgradHaloParams prm;
+  prm.tiles_n = (Cout + 63) / 64;
+  prm.tiles_w = W / WH_T; prm.tiles_h = H / WH_T;
+  prm.total_tiles = N * prm.tiles_w * prm.tiles_h;
+  int ksplit = num_sms() / prm.tiles_n;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > prm.total_tiles) ksplit = prm.total_tiles;
+  prm.tiles_per_split = (prm.total_tiles + ksplit - 1) / ksplit;
+  ksplit = (prm.total_tiles + prm.tiles_per_split - 1) / prm.tiles_per_split;
+  prm.num_items = prm.tiles_n * ksplit;
+  prm.Cout = Cout; prm.dW = dw; prm.scale = scale;
+  map_nhwc(&prm.mapX, x, N, H, W, 64, WH_PITCH, WH_PITCH, 1);
+  map_nhwc(&prm.mapZ, dz, N, H, W, Cout, WH_T, WH_T, 1);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM);
+    if (e != cudaSuccess)
+      throw std::runtime_error(std::string("[b200] cudaFuncSetAttribute(wgrad halo): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid(prm.num_items < num_sms() ? prm.num_items : num_sms());
+  wgrad_halo64_kernel<<<grid, UMMA_THREADS, WH_SMEM, stream>>>(prm);
+  count_launch();
+  check_last("wgrad_halo64_kernel launch");
+}
+
 void conv3x3_wgrad(const bf16* dz, const bf16* x, float* dw, int N, int H, int W, int Cin,
                    int Cout, float scale, int ksplit, int bn, cudaStream_t stream) {
   check_channels(Cin, "conv3x3_wgrad Cin");
   check_channels(Cout, "conv3x3_wgrad Cout");
+  if (Cin == 64 && H % WH_T == 0 && W % WH_T == 0 && W >= 16 && halo_enabled() && bn == 0 && ksplit <= 0) {
+    wgrad_halo64_launch(dz, x, dw, N, H, W, Cout, scale, stream);
+    return;
+  }
   WgradParams prm;
   prm.t = make_tile(N, H, W, 64);
   const int tiles_n = (N + prm.t.Nb - 1) / prm.t.Nb;
