@@ -92,6 +92,9 @@ def build_parser() -> argparse.ArgumentParser:
                      help="replay the reference's identical-shuffle-every-epoch behaviour")
     ext.add_argument("--shard-eval", action="store_true",
                      help="shard validation across ranks and all-reduce the metrics")
+    ext.add_argument("--class-weights", default=None,
+                     help="comma-separated per-class loss weights (the reference's commented-out "
+                          "CLASS_OPTIM_WEIGHTS, distributedUtil.py:27-28)")
     ext.add_argument("--profile", default=None, choices=[None, "events", "nvtx"],
                      help="events: per-phase CUDA-event timings each epoch; nvtx: emit NVTX ranges")
     ext.add_argument("--log-jsonl", default=None, help="append one JSON record per epoch")

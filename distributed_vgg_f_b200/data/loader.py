@@ -198,7 +198,7 @@ class DataManager:
 
     def __init__(self, root_folder: str, mini_batch: int, train: bool = True, *,
                  world_size: int = 1, rank: int = 0, pipeline: str = "fused", seed: int = 0,
-                 reference_order: bool = False, decode_threads: int = 8) -> None:
+                 reference_order: bool = False, decode_threads: int = 8, shard_eval: bool = False) -> None:
         if root_folder is None:
             raise ValueError("-rd/--root_dir is required")
         self.root_folder, self.mb_size, self.train = root_folder, mini_batch, train
@@ -210,6 +210,8 @@ class DataManager:
         if train and world_size > 1:      # validation is NOT sharded (distributedVggf.py:115)
             sampler = ShardedSampler(self.data_size, world_size, rank, seed=seed,
                                      reference_order=reference_order)
+        elif shard_eval and world_size > 1:   # extension: exact partition, metrics all-reduced
+            sampler = ShardedSampler(self.data_size, world_size, rank, shuffle=False, pad=False)
         if pipeline == "fused":
             self.cache = DecodedCache(self.samples, decode_threads)
             self.loader = _FusedLoader(self.cache, mini_batch, train, sampler, True, seed)

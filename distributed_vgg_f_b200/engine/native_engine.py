@@ -99,6 +99,7 @@ class NativeEngine:
         self.train_dropout = True        # tests switch dropout off to compare gradients exactly
         self.apply_updates = True        # False: leave raw gradients in g32 (gradient inspection)
         self.meter: Optional[DeviceMeter] = None
+        self.class_weights: Optional[torch.Tensor] = None
         self.timer = PhaseTimer(profile == "events")
         self.nvtx = profile == "nvtx"
         self.world = dist.get_world_size() if (distributed and distributed_is_initialized()) else 1
@@ -131,6 +132,10 @@ class NativeEngine:
             self.arena = SymmetricArena(n, dev, wire_dtype=wdt)
         if self.world > 1:
             self._broadcast_params()
+        # buckets holding only FC weight gradients are written with plain stores by the wgrad GEMM:
+        # the optimizer does not need to re-zero them (conv / bias gradients accumulate with red.add)
+        fc_w = {f.name + ".weight" for f in spec.fcs}
+        self._bucket_store_only = [all(t in fc_w for t in bk.tensors) for bk in self.plan.buckets]
         # FC weights that span whole buckets by themselves can be produced directly as bf16 on the wire
         self._prepacked = set()
         self._bucket_prepacked = [False] * len(self.plan.buckets)
@@ -450,8 +455,8 @@ class NativeEngine:
         bk = self.plan.buckets[bi]
         s, e = bk.start, bk.end
         if self.world == 1:
-            if self.apply_updates:
-                self._apply_update(s, e, None)   # same stream, right behind the producing kernels
+            if self.apply_updates:               # same stream, right behind the producing kernels
+                self._apply_update(s, e, None, zero=not self._bucket_store_only[bi])
             return
         ev = torch.cuda.Event()
         ev.record()
@@ -472,7 +477,8 @@ class NativeEngine:
             self.arena.allreduce(None if prepacked else self.g32, self.g32 if to_f32 else None, s, e - s,
                                  algo=algo, slot=bi % self.arena.slots, max_ctas=self.comm_ctas)
             if self.apply_updates:
-                self._apply_update(s, e, None if to_f32 else self.arena.wire[s:e], zero=not prepacked)
+                self._apply_update(s, e, None if to_f32 else self.arena.wire[s:e],
+                                   zero=not (prepacked or self._bucket_store_only[bi]))
 
     def _end_step(self) -> None:
         if self.world > 1:
@@ -481,6 +487,10 @@ class NativeEngine:
     # ================================================================================ public
     def set_meter(self, meter: Optional[DeviceMeter]) -> None:
         self.meter = meter
+
+    def set_class_weights(self, weights: Optional[torch.Tensor]) -> None:
+        """Per-class loss weights (the reference's optional weighted cross-entropy)."""
+        self.class_weights = None if weights is None else weights.to(self.device, F32).contiguous()
 
     def train_step(self, batch) -> torch.Tensor:
         """One optimisation step.  Returns the device scalar holding this batch's mean loss."""
@@ -495,7 +505,8 @@ class NativeEngine:
         self._forward(b, train=True)
         ld = self.fc_dz[-1].shape[1]
         meter = self.meter.buf if self.meter is not None else self.scratch_meter
-        ops.cross_entropy(self.logits[:b], self.labels_dev[:b], self.fc_dz[-1][:b], ld, meter, self.loss_buf)
+        ops.cross_entropy(self.logits[:b], self.labels_dev[:b], self.fc_dz[-1][:b], ld, meter, self.loss_buf,
+                          class_weights=self.class_weights)
         self._release_input()
         t.stop("forward")
         t.start("backward+reduce+update")

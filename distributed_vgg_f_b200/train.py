@@ -59,7 +59,8 @@ def manage_training(args) -> Trainer:
     dm_kw = dict(world_size=args.world_size, rank=args.rank, pipeline=args.pipeline,
                  seed=args.seed, reference_order=args.reference_order)
     train_data_mngr = DataManager(args.root_dir, args.mini_batch, train=True, **dm_kw)
-    valid_data_mngr = DataManager(args.root_dir, args.mini_batch, train=False, **dm_kw)
+    valid_data_mngr = DataManager(args.root_dir, args.mini_batch, train=False,
+                                  shard_eval=getattr(args, "shard_eval", False), **dm_kw)
     train_loader, valid_loader = train_data_mngr.get_loader(), valid_data_mngr.get_loader()
 
     num_classes = args.num_classes or train_data_mngr.number_classes
@@ -113,7 +114,12 @@ def manage_training(args) -> Trainer:
             with open(args.log_jsonl, "a") as f:
                 f.write(json.dumps(rec) + "\n")
 
-    trainer = Trainer(model, optimizer, train_loader, valid_loader, device,
-                      on_epoch_end=on_epoch_end)
+    cw = None
+    if getattr(args, "class_weights", None):
+        cw = torch.tensor([float(v) for v in args.class_weights.split(",")], dtype=torch.float32)
+        if cw.numel() != num_classes:
+            raise ValueError("--class-weights needs %d comma-separated values" % num_classes)
+    trainer = Trainer(model, optimizer, train_loader, valid_loader, device, class_weights=cw,
+                      on_epoch_end=on_epoch_end, shard_eval=getattr(args, "shard_eval", False))
     trainer.fit(args.epochs, start_epoch=start_epoch)
     return trainer

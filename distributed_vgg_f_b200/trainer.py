@@ -32,7 +32,7 @@ def _is_native(model) -> bool:
 class Trainer:
     def __init__(self, model, optimizer, train_loader, test_loader, device,
                  class_weights: Optional[torch.Tensor] = None, verbose_throughput: bool = True,
-                 on_epoch_end=None) -> None:
+                 on_epoch_end=None, shard_eval: bool = False) -> None:
         self.model = model
         self.optimizer = optimizer
         self.train_loader = train_loader
@@ -42,6 +42,9 @@ class Trainer:
         self.class_weights = class_weights.to(device) if class_weights is not None else None
         self.verbose_throughput = verbose_throughput
         self.on_epoch_end = on_epoch_end
+        self.shard_eval = shard_eval
+        if self.class_weights is not None and _is_native(model):
+            model.set_class_weights(self.class_weights)
         self.history = []
 
     # ------------------------------------------------------------------------------------------
@@ -102,6 +105,14 @@ class Trainer:
             meter.add_reference(outputs.detach(), targets)
         return meter.snapshot()
 
+    def _reduce_eval(self, meter: DeviceMeter):
+        """--shard-eval: every rank saw a disjoint slice of the validation set; sum the counters."""
+        import torch.distributed as dist
+
+        if self.shard_eval and dist.is_available() and dist.is_initialized():
+            dist.all_reduce(meter.buf)
+        return meter.snapshot()
+
     def _evaluate(self):
         meter = DeviceMeter(self.device)
         if _is_native(self.model):
@@ -109,7 +120,7 @@ class Trainer:
             for batch in self.test_loader:
                 self.model.eval_step(batch)
             self.model.sync()
-            return meter.snapshot()
+            return self._reduce_eval(meter)
 
         self.model.eval()
         with torch.no_grad():
@@ -117,4 +128,4 @@ class Trainer:
                 inputs, targets = self._to_device(batch)
                 outputs = self.model(inputs)
                 meter.add_reference(outputs, targets)
-        return meter.snapshot()
+        return self._reduce_eval(meter)

@@ -125,3 +125,36 @@ def _engine_worker(rank, world, algo):
 @pytest.mark.parametrize("algo", ["auto", "twoshot", "oneshot"])
 def test_engine_data_parallel_equivalence(algo):
     _run(_engine_worker, 2, algo)
+
+
+# ------------------------------------------------------------------------- barrier stress test
+def _stress_worker(rank, world):
+    """Random per-rank delays before back-to-back all-reduces on ONE slot: a flag-reuse or
+    missing-fence bug shows up as a wrong sum or a barrier timeout trap."""
+    import random
+
+    import torch.distributed as dist
+
+    from distributed_vgg_f_b200.parallel.symm import SymmetricArena
+
+    dev = torch.device("cuda", rank)
+    n = 1 << 20
+    arena = SymmetricArena(n, dev)
+    rng = random.Random(1234 + rank)
+    algos = ["oneshot", "twoshot"] + (["nvls"] if arena.has_multicast else [])
+    for it in range(60):
+        algo = algos[it % len(algos)]
+        g = torch.full((n,), float((rank + 1) * (it % 7 + 1)), device=dev)
+        out = torch.zeros(n, device=dev)
+        if rng.random() < 0.5:
+            torch.cuda._sleep(int(rng.random() * 3e6))          # up to ~1.5 ms of skew
+        m = 8 * rng.randrange(1, n // 8)
+        arena.allreduce(g, out, 0, m, algo=algo, slot=0, max_ctas=rng.choice([1, 4, 16]))
+        expect = (it % 7 + 1) * (world + 1) / 2.0
+        torch.cuda.synchronize(dev)
+        assert float((out[:m] - expect).abs().max()) < 0.05 * expect, (it, algo)
+        assert float(out[m:].abs().max()) == 0.0
+
+
+def test_allreduce_barrier_stress():
+    _run(_stress_worker, min(torch.cuda.device_count(), 8))
