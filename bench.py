@@ -167,19 +167,48 @@ def run_native(args):
                          lambda k: eng.train_step(dev_batches[k % len(dev_batches)]), args.steps)
     launches = ops.launch_count() - l0
 
-    # end-to-end: pinned host batch -> H2D every step, loss -> D2H every step
+    # end-to-end through the public API: DataManager (decoded uint8 cache -> pinned batch ring filled
+    # by the prefetch thread) -> engine.train_step(batch): every step copies its inputs host->device
+    # and reads the step's loss back device->host.
+    from distributed_vgg_f_b200.data.loader import DataManager
+    from distributed_vgg_f_b200.data.synthetic import make_synthetic_imagefolder
+
+    e2e_epoch_steps = min(args.steps, 16)
+    root = os.path.join("/tmp", "b200_bench_synth_ws%d_b%d_s%d" % (world, args.batch, e2e_epoch_steps))
+    if local == 0 and not os.path.isdir(os.path.join(root, "TrainData")):
+        ncls = min(args.num_classes, 16)
+        per_class = (e2e_epoch_steps * args.batch * world + ncls - 1) // ncls
+        make_synthetic_imagefolder(root + ".tmp", classes=["c%02d" % i for i in range(ncls)],
+                                   train_per_class=per_class, val_per_class=1, size=128, seed=7)
+        os.replace(root + ".tmp", root)
+    if world > 1:
+        dist.barrier()
+    dm = DataManager(root, args.batch, train=True, world_size=world, rank=rank, seed=0)
+    loader = dm.get_loader()
     loss_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
-    for k in range(min(args.warmup, 3)):
-        eng.train_step(host[k % len(host)])
+
+    def batches():
+        ep = 0
+        while True:
+            loader.set_epoch(ep)
+            for b in loader:
+                if b.labels.shape[0] == args.batch:
+                    yield b
+            ep += 1
+
+    gen = batches()
+    for k in range(3):
+        eng.train_step(next(gen))
     torch.cuda.synchronize(device)
 
     def e2e_step(k):
-        loss = eng.train_step(host[k % len(host)])
+        loss = eng.train_step(next(gen))
         loss_host[k:k + 1].copy_(loss, non_blocking=True)
 
     ms_e2e, wall_e2e = timed_region(torch, dist, world, device, e2e_step, args.steps)
     clk = clocks.stop()
-    h2d = host[0].images_u8.numel() + host[0].params.numel() * 4 + host[0].labels.numel() * 8
+    b0 = host[0]
+    h2d = b0.images_u8.numel() + b0.params.numel() * 4 + b0.labels.numel() * 8
 
     gb = args.batch * world
     value = gb * args.steps / (ms / 1e3)
@@ -200,7 +229,8 @@ def run_native(args):
                                     "4 distinct input batches rotated"},
             "e2e": {"value": round(e2e, 2), "unit": "images/sec", "ms_per_step": round(max(ms_e2e, wall_e2e) / args.steps, 4),
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                    "api": "NativeEngine.train_step(FusedBatch in pinned host memory) + async loss read-back"},
+                    "api": "DataManager(ImageFolder on disk, decoded uint8 cache, pinned ring) -> "
+                           "NativeEngine.train_step(batch) + async loss read-back"},
             "gpu_launches": int(launches), "clocks": clk,
             "final_loss": float(loss_host[-1]),
         }

@@ -49,7 +49,14 @@ for i, c in enumerate(spec.convs):
         rows.append(("conv0 fprop(im2col gemm)", t, 2.0 * M * 64 * 27 / 1e12, (M * 64 * 2 * 2) / 1e9))
         t = timeit(lambda: ops.gemm(dz0, col, dw0, M=64, N=64, K=M, a_mn=True, b_mn=True, epi="f32_atomic", ksplit=296, ldo=64))
         rows.append(("conv0 wgrad(gemm)", t, 2.0 * M * 64 * 27 / 1e12, (M * 64 * 2 * 2) / 1e9))
-        del col, y0, dz0
+        x4 = torch.randn(B, h, h, 4, device=dev).bfloat16()
+        yy = torch.empty(B, h, h, 64, dtype=torch.bfloat16, device=dev)
+        Cx = ops.require()
+        t = timeit(lambda: Cx.conv0_fprop(x4, w0, b0, yy))
+        rows.append(("conv0 fprop fused (no im2col)", t, 2.0 * M * 64 * 27 / 1e12, (M * 64 * 2) / 1e9))
+        t = timeit(lambda: Cx.conv0_wgrad(dz0.view(B, h, h, 64), x4, dw0))
+        rows.append(("conv0 wgrad fused (no im2col)", t, 2.0 * M * 64 * 27 / 1e12, (M * 64 * 2) / 1e9))
+        del col, y0, dz0, x4, yy
     else:
         x = torch.randn(B, h, h, c.cin, device=dev).bfloat16()
         w = (torch.randn(c.cout, 3, 3, c.cin, device=dev) * 0.05).bfloat16()

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 200 python bench/probe_shift.py > gpurun_out/probe_shift.log 2>&1; echo "== probe exit $?"
-for grp in "gemm" "conv" "augment or bias_grad or maxpool"; do
+
+for grp in "gemm" "conv" "augment or bias_grad or maxpool or conv0"; do
   name=$(echo "$grp" | tr ' ' '_')
   timeout 300 python -m pytest tests/test_kernels_gpu.py -q --tb=short -m gpu -k "$grp" > "gpurun_out/k_${name}.log" 2>&1
   echo "== $grp: exit $?"; tail -n 2 "gpurun_out/k_${name}.log"

@@ -58,6 +58,19 @@ static void conv_wgrad(const at::Tensor& dz, const at::Tensor& x, at::Tensor dw,
   b200::conv3x3_wgrad(bfp(dz), bfp(x), f32p(dw), N, H, W, Cin, Cout, (float)scale, (int)ksplit, (int)bn, cur_stream());
 }
 
+static void conv0_fprop(const at::Tensor& x4, const at::Tensor& w0, const at::Tensor& bias, at::Tensor y) {
+  c10::cuda::CUDAGuard g(x4.device());
+  TORCH_CHECK(x4.dim() == 4 && x4.size(3) == 4 && x4.is_contiguous() && w0.numel() == 64 * 64 && y.is_contiguous(),
+              "conv0_fprop: x4 [N,H,W,4], w0 [64,64]");
+  b200::conv0_fprop(bfp(x4), bfp(w0), f32p(bias), bfp_mut(y), x4.size(0), x4.size(1), x4.size(2), cur_stream());
+}
+static void conv0_wgrad(const at::Tensor& dz, const at::Tensor& x4, at::Tensor dw0) {
+  c10::cuda::CUDAGuard g(x4.device());
+  TORCH_CHECK(x4.dim() == 4 && x4.size(3) == 4 && x4.is_contiguous() && dz.is_contiguous() && dw0.numel() == 64 * 64,
+              "conv0_wgrad: x4 [N,H,W,4], dw0 [64,64]");
+  b200::conv0_wgrad(bfp(dz), bfp(x4), f32p(dw0), x4.size(0), x4.size(1), x4.size(2), cur_stream());
+}
+
 static void shift_probe(const at::Tensor& A, const at::Tensor& B, at::Tensor out, int64_t shift, int64_t pitch,
                         bool use_base_offset, int64_t mode) {
   c10::cuda::CUDAGuard g(A.device());
@@ -191,6 +204,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("launch_count", &b200::launch_count);
   m.def("gemm", &gemm);
   m.def("shift_probe", &shift_probe);
+  m.def("conv0_fprop", &conv0_fprop);
+  m.def("conv0_wgrad", &conv0_wgrad);
   m.def("conv_fprop", &conv_fprop);
   m.def("conv_dgrad", &conv_dgrad);
   m.def("conv_wgrad", &conv_wgrad);

@@ -21,6 +21,12 @@ void gemm_bf16(const bf16* A, long long lda, bool a_mn, const bf16* B, long long
                int M, int N, int K, void* out, long long ldo, int epi, const float* bias,
                float alpha, int ksplit, int bn, cudaStream_t stream);
 
+// First convolution (3 -> 64 channels) straight from NHWC4 pixels: the im2col operand tile is built
+// in shared memory by producer warps (conv0.cuh).  w0 is [64][64] bf16 (k = (kh*3+kw)*3+c, zero tail).
+void conv0_fprop(const bf16* x4, const bf16* w0, const float* bias, bf16* y, int N, int H, int W,
+                 cudaStream_t stream);
+void conv0_wgrad(const bf16* dz, const bf16* x4, float* dw0, int N, int H, int W, cudaStream_t stream);
+
 // 3x3 / stride 1 / pad 1 convolution, NHWC bf16, weights [Cout][3][3][Cin] bf16.
 void conv3x3_fprop(const bf16* x, const bf16* w, const float* bias, bf16* y, int N, int H, int W,
                    int Cin, int Cout, bool relu, int bn, cudaStream_t stream);

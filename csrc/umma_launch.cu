@@ -10,6 +10,7 @@
 #include <string>
 
 #include "api.h"
+#include "conv0.cuh"
 #include "conv_halo.cuh"
 #include "wgrad_halo.cuh"
 #include "umma_policies.cuh"
@@ -164,6 +165,48 @@ static void conv_halo_launch(ConvParams& prm, const bf16* act, cudaStream_t stre
   conv_halo_kernel<BN, DGRAD><<<grid, UMMA_THREADS, smem, stream>>>(prm);
   count_launch();
   check_last("conv_halo_kernel launch");
+}
+
+// ------------------------------------------------------------------------- first conv (no im2col)
+template <bool WGRAD>
+static void conv0_launch(Conv0Params& prm, int grid, cudaStream_t stream) {
+  constexpr int stage = C0_TILE_BYTES + (WGRAD ? 2 * UMMA_SLAB_BYTES : 0);
+  constexpr int smem = C0_STAGES * stage + 8192 + 512 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv0_kernel<WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess)
+      throw std::runtime_error(std::string("[b200] cudaFuncSetAttribute(conv0): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  conv0_kernel<WGRAD><<<grid, C0_THREADS, smem, stream>>>(prm);
+  count_launch();
+  check_last("conv0_kernel launch");
+}
+
+void conv0_fprop(const bf16* x4, const bf16* w0, const float* bias, bf16* y, int N, int H, int W,
+                 cudaStream_t stream) {
+  Conv0Params prm;
+  prm.x4 = x4; prm.out = y; prm.bias = bias; prm.dW = nullptr;
+  prm.N = N; prm.H = H; prm.W = W; prm.pixels = static_cast<long long>(N) * H * W;
+  prm.num_tiles = static_cast<int>((prm.pixels + 127) / 128);
+  prm.blocks_per_cta = 0;
+  map_2d(&prm.mapW, w0, 64, 64, 64, 64, 64);
+  prm.mapZ = prm.mapW;
+  conv0_launch<false>(prm, prm.num_tiles < num_sms() ? prm.num_tiles : num_sms(), stream);
+}
+
+void conv0_wgrad(const bf16* dz, const bf16* x4, float* dw0, int N, int H, int W, cudaStream_t stream) {
+  Conv0Params prm;
+  prm.x4 = x4; prm.out = nullptr; prm.bias = nullptr; prm.dW = dw0;
+  prm.N = N; prm.H = H; prm.W = W; prm.pixels = static_cast<long long>(N) * H * W;
+  prm.num_tiles = static_cast<int>((prm.pixels + 63) / 64);
+  int grid = prm.num_tiles < num_sms() ? prm.num_tiles : num_sms();
+  prm.blocks_per_cta = (prm.num_tiles + grid - 1) / grid;
+  grid = (prm.num_tiles + prm.blocks_per_cta - 1) / prm.blocks_per_cta;
+  map_2d(&prm.mapZ, dz, prm.pixels, 64, 64, 64, 64);
+  prm.mapW = prm.mapZ;
+  conv0_launch<true>(prm, grid, stream);
 }
 
 // ---------------------------------------------------------------------------------------- GEMM

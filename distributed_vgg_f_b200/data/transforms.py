@@ -30,40 +30,44 @@ def sample_train_params(n: int, src_h: int, src_w: int,
                         generator: Optional[torch.Generator] = None,
                         scale=DATA.crop_scale, ratio=DATA.crop_ratio,
                         degrees: float = DATA.rotation_deg) -> torch.Tensor:
-    """Random crop box / angle / flip per sample, distributed as torchvision's get_params."""
+    """Random crop box / angle / flip per sample, distributed as torchvision's get_params.
+
+    Vectorised over the batch (the loader thread must keep up with ~8k images/s per GPU):
+    RandomResizedCrop's "up to 10 attempts, else centre crop" becomes a first-valid-attempt select.
+    """
     out = torch.zeros(n, PARAM_DIM, dtype=torch.float32)
     area = float(src_h * src_w)
     log_lo, log_hi = math.log(ratio[0]), math.log(ratio[1])
-    u = torch.rand(n, 10, 2, generator=generator)
-    pos = torch.rand(n, 2, generator=generator)
-    misc = torch.rand(n, 2, generator=generator)
-    for s in range(n):
-        box = None
-        for t in range(10):
-            target_area = area * (scale[0] + (scale[1] - scale[0]) * float(u[s, t, 0]))
-            aspect = math.exp(log_lo + (log_hi - log_lo) * float(u[s, t, 1]))
-            w = int(round(math.sqrt(target_area * aspect)))
-            h = int(round(math.sqrt(target_area / aspect)))
-            if 0 < w <= src_w and 0 < h <= src_h:
-                i = min(int(float(pos[s, 0]) * (src_h - h + 1)), src_h - h)
-                j = min(int(float(pos[s, 1]) * (src_w - w + 1)), src_w - w)
-                box = (i, j, h, w)
-                break
-        if box is None:     # torchvision's centre-crop fallback
-            in_ratio = src_w / src_h
-            if in_ratio < min(ratio):
-                w = src_w
-                h = int(round(w / min(ratio)))
-            elif in_ratio > max(ratio):
-                h = src_h
-                w = int(round(h * max(ratio)))
-            else:
-                w, h = src_w, src_h
-            box = ((src_h - h) // 2, (src_w - w) // 2, h, w)
-        theta = math.radians(-degrees + 2.0 * degrees * float(misc[s, 0]))
-        out[s, 0], out[s, 1], out[s, 2], out[s, 3] = box
-        out[s, 4], out[s, 5] = math.cos(theta), math.sin(theta)
-        out[s, 6] = 1.0 if float(misc[s, 1]) < 0.5 else 0.0
+    u = torch.rand(n, 10, 2, generator=generator, dtype=torch.float64)
+    pos = torch.rand(n, 2, generator=generator, dtype=torch.float64)
+    misc = torch.rand(n, 2, generator=generator, dtype=torch.float64)
+    target_area = area * (scale[0] + (scale[1] - scale[0]) * u[..., 0])
+    aspect = torch.exp(log_lo + (log_hi - log_lo) * u[..., 1])
+    w = torch.round(torch.sqrt(target_area * aspect))                     # [n, 10]
+    h = torch.round(torch.sqrt(target_area / aspect))
+    ok = (w > 0) & (w <= src_w) & (h > 0) & (h <= src_h)
+    first = torch.argmax(ok.to(torch.int8), dim=1)                        # first valid attempt
+    any_ok = ok.any(dim=1)
+    rows = torch.arange(n)
+    cw, ch = w[rows, first], h[rows, first]
+    # torchvision's centre-crop fallback when all 10 attempts fail
+    in_ratio = src_w / src_h
+    if in_ratio < min(ratio):
+        fw, fh = float(src_w), float(round(src_w / min(ratio)))
+    elif in_ratio > max(ratio):
+        fh, fw = float(src_h), float(round(src_h * max(ratio)))
+    else:
+        fw, fh = float(src_w), float(src_h)
+    cw = torch.where(any_ok, cw, torch.full_like(cw, fw))
+    ch = torch.where(any_ok, ch, torch.full_like(ch, fh))
+    top = torch.minimum(torch.floor(pos[:, 0] * (src_h - ch + 1)), src_h - ch)
+    left = torch.minimum(torch.floor(pos[:, 1] * (src_w - cw + 1)), src_w - cw)
+    top = torch.where(any_ok, top, torch.floor((src_h - ch) / 2))
+    left = torch.where(any_ok, left, torch.floor((src_w - cw) / 2))
+    theta = torch.deg2rad(-degrees + 2.0 * degrees * misc[:, 0])
+    out[:, 0], out[:, 1], out[:, 2], out[:, 3] = top.float(), left.float(), ch.float(), cw.float()
+    out[:, 4], out[:, 5] = torch.cos(theta).float(), torch.sin(theta).float()
+    out[:, 6] = (misc[:, 1] < 0.5).float()
     return out
 
 

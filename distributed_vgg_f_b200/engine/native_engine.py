@@ -210,8 +210,11 @@ class NativeEngine:
         self._labels_dev = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(2)]
         self._in_free = [None, None]           # event: the step that used this slot is done with it
         self.labels_dev = self._labels_dev[0]
-        self.col0 = torch.empty(B * HW * HW, L.CONV0_K, dtype=BF16, device=dev)
-        self.x_nhwc = None
+        # first conv: fused kernels build the im2col operand in shared memory from NHWC4 pixels
+        # (csrc/include/conv0.cuh); the explicit im2col matrix only exists for other widths
+        self.fused_conv0 = spec.convs[0].cout == 64
+        self.col0 = None if self.fused_conv0 else torch.empty(B * HW * HW, L.CONV0_K, dtype=BF16, device=dev)
+        self.x_nhwc = torch.empty(B, HW, HW, 4, dtype=BF16, device=dev)
         self.acts: List[torch.Tensor] = []      # post-ReLU conv outputs
         self.pools: List[Optional[torch.Tensor]] = []
         h = HW
@@ -269,21 +272,19 @@ class NativeEngine:
             cur.wait_event(h2d)
             # two passes: transform once per pixel into 8-byte NHWC4 pixels (25 MB at B=64, L2
             # resident), then expand to the first conv's im2col rows with coalesced 16-byte stores
-            if self.x_nhwc is None:
-                self.x_nhwc = torch.empty(self.B, HW, HW, 4, dtype=BF16, device=self.device)
             ops.augment(self._src_u8[j][:b], self._params_dev[j][:b], self.x_nhwc[:b], batch.resized_hw,
                         out_hw=HW, mode="nhwc", pad=4)
-            C.im2col_c3(self.x_nhwc[:b], self.col0[:b * HW * HW], L.CONV0_K)
+            if not self.fused_conv0:
+                C.im2col_c3(self.x_nhwc[:b], self.col0[:b * HW * HW], L.CONV0_K)
             return b
         x, y = batch
         b = int(y.shape[0])
         x = x.to(self.device, F32, non_blocking=True).contiguous()
         assert x.shape[2] == HW and x.shape[3] == HW, "input size differs from the engine's input_hw"
         self.labels_dev[:b].copy_(y, non_blocking=True)
-        if self.x_nhwc is None:
-            self.x_nhwc = torch.empty(self.B, HW, HW, 4, dtype=BF16, device=self.device)
         C.nchw_to_nhwc(x, self.x_nhwc[:b])
-        C.im2col_c3(self.x_nhwc[:b], self.col0[:b * HW * HW], L.CONV0_K)
+        if not self.fused_conv0:
+            C.im2col_c3(self.x_nhwc[:b], self.col0[:b * HW * HW], L.CONV0_K)
         return b
 
     def _release_input(self) -> None:
@@ -308,9 +309,12 @@ class NativeEngine:
         spec, HW = self.spec, self.HW
         c0 = spec.convs[0]
         M0 = b * HW * HW
-        # conv0: im2col GEMM with fused bias + ReLU -> bf16 NHWC
-        ops.gemm(self.col0[:M0], self._w(c0.name), self.acts[0][:b].view(M0, c0.cout), M=M0, N=c0.cout,
-                 K=L.CONV0_K, epi="bf16_bias_relu", bias=self._b(c0.name), bn=64 if c0.cout == 64 else 0)
+        # conv0 (K = 27): im2col GEMM with fused bias + ReLU -> bf16 NHWC
+        if self.fused_conv0:
+            C.conv0_fprop(self.x_nhwc[:b], self._w(c0.name), self._b(c0.name), self.acts[0][:b])
+        else:
+            ops.gemm(self.col0[:M0], self._w(c0.name), self.acts[0][:b].view(M0, c0.cout), M=M0, N=c0.cout,
+                     K=L.CONV0_K, epi="bf16_bias_relu", bias=self._b(c0.name))
         x = self.acts[0][:b]
         if c0.pool_after:
             x = ops.maxpool2x2(x, out=self.pools[0][:b])
@@ -407,9 +411,12 @@ class NativeEngine:
                 ops.bias_grad(dz.view(M, c.cout), self._grad(c.name + ".bias"), M, c.cout)
             self._bucket_done(c.name + ".bias")
             if i == 0:
-                ks = max(1, min(M // 64, 296))
-                ops.gemm(dz.view(M, c.cout), self.col0[:M], self._grad(c.name + ".weight"), M=c.cout,
-                         N=L.CONV0_K, K=M, a_mn=True, b_mn=True, epi="f32_atomic", ksplit=ks, ldo=L.CONV0_K)
+                if self.fused_conv0:
+                    C.conv0_wgrad(dz, self.x_nhwc[:b], self._grad(c.name + ".weight"))
+                else:
+                    ks = max(1, min(M // 64, 296))
+                    ops.gemm(dz.view(M, c.cout), self.col0[:M], self._grad(c.name + ".weight"), M=c.cout,
+                             N=L.CONV0_K, K=M, a_mn=True, b_mn=True, epi="f32_atomic", ksplit=ks, ldo=L.CONV0_K)
                 self._bucket_done(c.name + ".weight")
                 break
             prev = convs[i - 1]

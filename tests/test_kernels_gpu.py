@@ -153,6 +153,33 @@ def test_conv_wgrad(N, H, W, Cin, Cout):
     assert rel_err(dw, ref) < 5e-3
 
 
+@pytest.mark.parametrize("N,H,W", [(2, 16, 16), (1, 30, 22), (3, 64, 64)])
+def test_conv0_fused(N, H, W):
+    """First conv straight from NHWC4 pixels (im2col tile built in shared memory): fprop + wgrad."""
+    ops = _ops()
+    C = ops.require()
+    torch.manual_seed(0)
+    x = bf(torch.randn(N, H, W, 3, device=DEV))
+    x4 = torch.zeros(N, H, W, 4, dtype=torch.bfloat16, device=DEV)
+    x4[..., :3] = x
+    w = bf(torch.randn(64, 3, 3, 3, device=DEV) * 0.2)           # [co][kh][kw][c]
+    w0 = torch.zeros(64, 64, dtype=torch.bfloat16, device=DEV)
+    w0[:, :27] = w.reshape(64, 27)
+    bias = torch.randn(64, device=DEV)
+    y = torch.empty(N, H, W, 64, dtype=torch.bfloat16, device=DEV)
+    C.conv0_fprop(x4, w0, bias, y)
+    xr = x.float().permute(0, 3, 1, 2)
+    wr = w.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    ref = torch.relu(F.conv2d(xr, wr, bias, padding=1))
+    assert rel_err(y, ref.permute(0, 2, 3, 1)) < 1e-2
+    dz = bf(torch.randn(N, H, W, 64, device=DEV))
+    dw0 = torch.zeros(64, 64, device=DEV)
+    C.conv0_wgrad(dz, x4, dw0)
+    F.conv2d(xr, wr, None, padding=1).backward(dz.float().permute(0, 3, 1, 2))
+    assert rel_err(dw0[:, :27], wr.grad.permute(0, 2, 3, 1).reshape(64, 27)) < 5e-3
+    assert torch.count_nonzero(dw0[:, 27:]) == 0
+
+
 # ------------------------------------------------------------------------------------- pointwise
 def test_maxpool_fwd_bwd():
     ops = _ops()
