@@ -172,6 +172,35 @@ static void nchw_to_nhwc(const at::Tensor& x, at::Tensor y) {
   b200::nchw_f32_to_nhwc_bf16(f32p(x), bfp_mut(y), x.size(0), x.size(1), x.size(2), x.size(3), y.size(3), cur_stream());
 }
 
+// ------------------------------------------------------------------------------------ PNG decode
+namespace b200 {
+struct PngImage {
+  int w = 0, h = 0;
+  std::vector<uint8_t> rgb;
+  bool ok = false;
+};
+void decode_png_files(const std::vector<std::string>& paths, int threads, std::vector<PngImage>& out);
+}  // namespace b200
+
+// All files decoded natively into one uint8 [N,H,W,3] tensor; throws if a file is not a plain 8-bit
+// PNG or the sizes differ (the caller then falls back to PIL).
+static at::Tensor decode_pngs(const std::vector<std::string>& paths, int64_t threads) {
+  std::vector<b200::PngImage> imgs;
+  {
+    py::gil_scoped_release nogil;
+    b200::decode_png_files(paths, (int)threads, imgs);
+  }
+  TORCH_CHECK(!imgs.empty(), "decode_pngs: no files");
+  const int w = imgs[0].w, h = imgs[0].h;
+  for (size_t i = 0; i < imgs.size(); ++i)
+    TORCH_CHECK(imgs[i].ok && imgs[i].w == w && imgs[i].h == h, "decode_pngs: unsupported or non-uniform file ", paths[i]);
+  at::Tensor out = at::empty({(int64_t)imgs.size(), h, w, 3}, at::kByte);
+  uint8_t* dst = out.data_ptr<uint8_t>();
+  const size_t per = (size_t)w * h * 3;
+  for (size_t i = 0; i < imgs.size(); ++i) memcpy(dst + i * per, imgs[i].rgb.data(), per);
+  return out;
+}
+
 // ------------------------------------------------------------------------------------------- comm
 struct PyComm {
   b200::CommCtx c;
@@ -202,6 +231,7 @@ static void barrier(const PyComm& comm, int64_t slot, int64_t epoch) {
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "distributed-vgg-f_b200 native sm_100a kernels";
   m.def("launch_count", &b200::launch_count);
+  m.def("decode_pngs", &decode_pngs);
   m.def("gemm", &gemm);
   m.def("shift_probe", &shift_probe);
   m.def("conv0_fprop", &conv0_fprop);

@@ -56,20 +56,22 @@ class DecodedCache:
 
     def __init__(self, samples: List[Tuple[str, int]], threads: int = 8) -> None:
         paths = [p for p, _ in samples]
-        arrays = None
+        images = None
         try:   # native multi-threaded PNG decode (csrc/png_decode.cpp), falls back to PIL
             from ..ops import native_decode_pngs
-            arrays = native_decode_pngs(paths, threads)
+            images = native_decode_pngs(paths, threads)
         except Exception:
-            arrays = None
-        if arrays is None:
+            images = None
+        self.native_decode = images is not None
+        if images is None:
             with ThreadPoolExecutor(max_workers=threads) as ex:
                 arrays = list(ex.map(_decode, paths))
-        shapes = {a.shape for a in arrays}
-        if len(shapes) != 1:
-            raise ValueError("fused pipeline needs a uniform image size, found %s; "
-                             "use pipeline='reference'" % sorted(shapes)[:4])
-        self.images = torch.from_numpy(np.stack(arrays))              # [N,H,W,3] uint8
+            shapes = {a.shape for a in arrays}
+            if len(shapes) != 1:
+                raise ValueError("fused pipeline needs a uniform image size, found %s; "
+                                 "use pipeline='reference'" % sorted(shapes)[:4])
+            images = torch.from_numpy(np.stack(arrays))
+        self.images = images                                          # [N,H,W,3] uint8
         self.labels = torch.tensor([l for _, l in samples], dtype=torch.int64)
         self.src_hw = (int(self.images.shape[1]), int(self.images.shape[2]))
 

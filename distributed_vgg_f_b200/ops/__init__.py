@@ -147,8 +147,14 @@ def augment(src_u8, params, out, resized_hw: Tuple[int, int], out_hw: int = DATA
 
 
 def native_decode_pngs(paths, threads: int = 8):
-    """Multi-threaded native PNG decode -> list of uint8 HWC numpy arrays, or None if unsupported."""
-    C = require()
-    if not hasattr(C, "decode_pngs"):
+    """Multi-threaded native PNG decode (csrc/png_decode.cpp) -> uint8 tensor [N,H,W,3], or None when
+    a file is not a plain 8-bit PNG / sizes differ / the extension is absent (caller uses PIL)."""
+    if _C is None or not hasattr(_C, "decode_pngs"):
         return None
-    return C.decode_pngs(list(paths), threads)
+    paths = list(paths)
+    if not paths or not all(p.lower().endswith(".png") for p in paths):
+        return None
+    try:
+        return _C.decode_pngs(paths, threads)
+    except Exception:
+        return None
