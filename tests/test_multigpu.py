@@ -140,16 +140,17 @@ def _stress_worker(rank, world):
     dev = torch.device("cuda", rank)
     n = 1 << 20
     arena = SymmetricArena(n, dev)
-    rng = random.Random(1234 + rank)
+    skew = random.Random(1234 + rank)          # per-rank: who is late, and by how much
+    plan = random.Random(99)                   # shared: every rank must launch the SAME collective
     algos = ["oneshot", "twoshot"] + (["nvls"] if arena.has_multicast else [])
     for it in range(60):
         algo = algos[it % len(algos)]
         g = torch.full((n,), float((rank + 1) * (it % 7 + 1)), device=dev)
         out = torch.zeros(n, device=dev)
-        if rng.random() < 0.5:
-            torch.cuda._sleep(int(rng.random() * 3e6))          # up to ~1.5 ms of skew
-        m = 8 * rng.randrange(1, n // 8)
-        arena.allreduce(g, out, 0, m, algo=algo, slot=0, max_ctas=rng.choice([1, 4, 16]))
+        if skew.random() < 0.5:
+            torch.cuda._sleep(int(skew.random() * 3e6))         # up to ~1.5 ms of skew
+        m = 8 * plan.randrange(1, n // 8)
+        arena.allreduce(g, out, 0, m, algo=algo, slot=0, max_ctas=plan.choice([1, 4, 16]))
         expect = (it % 7 + 1) * (world + 1) / 2.0
         torch.cuda.synchronize(dev)
         assert float((out[:m] - expect).abs().max()) < 0.05 * expect, (it, algo)
