@@ -2,7 +2,7 @@
 //
 // The first version expanded the 3-channel image into im2col rows [pixels][64] in global memory
 // (411 MB written by the input kernel, read by the fprop GEMM, read again by the wgrad GEMM).  Here
-// four producer warps build the 128B-swizzled operand tile DIRECTLY IN SHARED MEMORY from the
+// eight producer warps build the 128B-swizzled operand tile DIRECTLY IN SHARED MEMORY from the
 // 8-byte NHWC4 pixels (row = pixel, 64 bf16 = 27 taps*channels + zero tail; 16-byte chunk j of row r
 // lives at r*128 + ((j ^ (r & 7)) << 4), exactly what a SWIZZLE_128B TMA load would have written),
 // make it visible to the async proxy (fence.proxy.async) and hand it to tcgen05.mma through the
@@ -18,7 +18,7 @@ namespace b200 {
 
 constexpr int C0_STAGES = 4;
 constexpr int C0_PROD_WARPS = 8;                                  // 256 producer threads, in row-groups
-constexpr int C0_THREADS = UMMA_THREADS + 32 * C0_PROD_WARPS;     // 10 + 4 warps
+constexpr int C0_THREADS = UMMA_THREADS + 32 * C0_PROD_WARPS;     // 10 + 8 warps
 constexpr int C0_TILE_BYTES = 128 * 128;                          // 128 rows x 64 bf16
 
 struct Conv0Params {
