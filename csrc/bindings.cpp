@@ -201,6 +201,69 @@ static at::Tensor decode_pngs(const std::vector<std::string>& paths, int64_t thr
   return out;
 }
 
+// ------------------------------------------------------------------------------- batch prefetcher
+namespace b200 {
+struct PrefetchConfig {
+  const uint8_t* cache;
+  const int64_t* labels;
+  int H, W, mb, slots;
+  uint8_t* ring_img;
+  float* ring_par;
+  int64_t* ring_lab;
+  bool train;
+  float scale_lo, scale_hi, ratio_lo, ratio_hi, degrees;
+};
+class BatchPrefetcher;
+BatchPrefetcher* prefetcher_create(const PrefetchConfig& c);
+void prefetcher_destroy(BatchPrefetcher* p);
+void prefetcher_start(BatchPrefetcher* p, std::vector<int64_t> idx, uint64_t seed);
+bool prefetcher_next(BatchPrefetcher* p, int& slot, int& count);
+void prefetcher_release(BatchPrefetcher* p, int slot, uint64_t cuda_event);
+void prefetcher_stop(BatchPrefetcher* p);
+}  // namespace b200
+
+struct PyPrefetcher {
+  b200::BatchPrefetcher* p = nullptr;
+  at::Tensor cache, labels, ring_img, ring_par, ring_lab;     // keep the storage alive
+  PyPrefetcher(at::Tensor cache_, at::Tensor labels_, at::Tensor ring_img_, at::Tensor ring_par_, at::Tensor ring_lab_,
+               bool train, double scale_lo, double scale_hi, double ratio_lo, double ratio_hi, double degrees)
+      : cache(cache_), labels(labels_), ring_img(ring_img_), ring_par(ring_par_), ring_lab(ring_lab_) {
+    TORCH_CHECK(cache.dim() == 4 && cache.size(3) == 3 && cache.scalar_type() == at::kByte && cache.is_contiguous() &&
+                !cache.is_cuda(), "Prefetcher: cache must be a CPU uint8 [N,H,W,3] tensor");
+    TORCH_CHECK(ring_img.dim() == 5 && ring_img.is_contiguous() && ring_par.is_contiguous() && ring_lab.is_contiguous() &&
+                labels.scalar_type() == at::kLong && ring_lab.scalar_type() == at::kLong && ring_par.scalar_type() == at::kFloat,
+                "Prefetcher: bad ring tensors");
+    b200::PrefetchConfig c;
+    c.cache = cache.data_ptr<uint8_t>(); c.labels = labels.data_ptr<int64_t>();
+    c.H = (int)cache.size(1); c.W = (int)cache.size(2);
+    c.slots = (int)ring_img.size(0); c.mb = (int)ring_img.size(1);
+    c.ring_img = ring_img.data_ptr<uint8_t>(); c.ring_par = ring_par.data_ptr<float>(); c.ring_lab = ring_lab.data_ptr<int64_t>();
+    c.train = train; c.scale_lo = (float)scale_lo; c.scale_hi = (float)scale_hi;
+    c.ratio_lo = (float)ratio_lo; c.ratio_hi = (float)ratio_hi; c.degrees = (float)degrees;
+    p = b200::prefetcher_create(c);
+  }
+  ~PyPrefetcher() { if (p) b200::prefetcher_destroy(p); }
+  void start(std::vector<int64_t> idx, uint64_t seed) {
+    py::gil_scoped_release nogil;
+    b200::prefetcher_start(p, std::move(idx), seed);
+  }
+  py::object next() {
+    int slot = -1, count = 0;
+    bool ok;
+    {
+      py::gil_scoped_release nogil;
+      ok = b200::prefetcher_next(p, slot, count);
+    }
+    if (!ok) return py::none();
+    return py::make_tuple(slot, count);
+  }
+  void release(int64_t slot, uint64_t ev) { b200::prefetcher_release(p, (int)slot, ev); }
+  void stop() {
+    py::gil_scoped_release nogil;
+    b200::prefetcher_stop(p);
+  }
+};
+
 // ------------------------------------------------------------------------------------------- comm
 struct PyComm {
   b200::CommCtx c;
@@ -254,6 +317,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("augment", &augment);
   m.def("im2col_c3", &im2col_c3);
   m.def("nchw_to_nhwc", &nchw_to_nhwc);
+  py::class_<PyPrefetcher>(m, "Prefetcher")
+      .def(py::init<at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, bool, double, double, double, double, double>())
+      .def("start", &PyPrefetcher::start)
+      .def("next", &PyPrefetcher::next)
+      .def("release", &PyPrefetcher::release)
+      .def("stop", &PyPrefetcher::stop);
   py::class_<PyComm>(m, "Comm");
   m.def("make_comm", &make_comm);
   m.def("allreduce", &allreduce);

@@ -77,8 +77,13 @@ class DecodedCache:
 
 
 class _FusedLoader:
+    """Batches for the fused GPU pipeline.  With the native extension present, a C++ worker thread
+    (csrc/prefetch.cpp) gathers images from the decoded cache into a pinned ring and draws the
+    transform parameters without ever taking the GIL; otherwise a Python thread does the same."""
+
     def __init__(self, cache: DecodedCache, mb: int, train: bool, sampler: Optional[ShardedSampler],
-                 shuffle: bool, seed: int, prefetch: int = 2, pin: Optional[bool] = None) -> None:
+                 shuffle: bool, seed: int, prefetch: int = 3, pin: Optional[bool] = None,
+                 native: Optional[bool] = None) -> None:
         self.cache, self.mb, self.train = cache, mb, train
         self.sampler, self.shuffle, self.seed = sampler, shuffle, seed
         self.prefetch = prefetch
@@ -86,13 +91,25 @@ class _FusedLoader:
         self.epoch = 0
         H, W = cache.src_hw
         self.resized_hw = T.resized_dims(train, H, W)
-        self._ring = []
-        self._state = []
-        for _ in range(prefetch + 1):
-            self._ring.append((self._buf((mb, H, W, 3), torch.uint8),
-                               self._buf((mb, T.PARAM_DIM), torch.float32),
-                               self._buf((mb,), torch.int64)))
-            self._state.append({})
+        slots = prefetch + 1
+        self._img = self._buf((slots, mb, H, W, 3), torch.uint8)
+        self._par = self._buf((slots, mb, T.PARAM_DIM), torch.float32)
+        self._lab = self._buf((slots, mb), torch.int64)
+        self._ring = [(self._img[s], self._par[s], self._lab[s]) for s in range(slots)]
+        self._state = [{} for _ in range(slots)]
+        self._pf = None
+        if native is None or native:
+            try:
+                from .. import ops
+                if ops.available() and hasattr(ops.require(), "Prefetcher"):
+                    self._pf = ops.require().Prefetcher(
+                        cache.images, cache.labels, self._img, self._par, self._lab, train,
+                        DATA.crop_scale[0], DATA.crop_scale[1], DATA.crop_ratio[0], DATA.crop_ratio[1],
+                        DATA.rotation_deg)
+            except Exception:
+                if native:
+                    raise
+                self._pf = None
 
     def _buf(self, shape, dtype):
         t = torch.empty(shape, dtype=dtype)
@@ -116,10 +133,39 @@ class _FusedLoader:
             return torch.randperm(n, generator=g).tolist()
         return list(range(n))
 
+    def _epoch_seed(self) -> int:
+        return 1_000_003 * (self.seed + 1) + self.epoch * 7919 + (self.sampler.rank if self.sampler else 0)
+
     def __iter__(self) -> Iterator[FusedBatch]:
+        if self._pf is not None:
+            return self._iter_native()
+        return self._iter_python()
+
+    # -- native worker thread ---------------------------------------------------------------------
+    def _iter_native(self) -> Iterator[FusedBatch]:
+        self._pf.start(self._indices(), self._epoch_seed())
+        prev = None
+        try:
+            while True:
+                item = self._pf.next()           # blocks with the GIL released
+                if prev is not None:             # consumer asked for more: previous slot may be refilled
+                    ev = self._state[prev].pop("event", None)
+                    self._state[prev]["held"] = ev          # keep the event alive until the worker used it
+                    self._pf.release(prev, int(ev.cuda_event) if ev is not None else 0)
+                    prev = None
+                if item is None:
+                    break
+                slot, k = item
+                img, par, lab = self._ring[slot]
+                prev = slot
+                yield FusedBatch(img[:k], par[:k], lab[:k], self.resized_hw, self._state[slot])
+        finally:
+            self._pf.stop()
+
+    # -- Python fallback ---------------------------------------------------------------------------
+    def _iter_python(self) -> Iterator[FusedBatch]:
         idx = self._indices()
-        gen = torch.Generator().manual_seed(1_000_003 * (self.seed + 1) + self.epoch * 7919 +
-                                            (self.sampler.rank if self.sampler else 0))
+        gen = torch.Generator().manual_seed(self._epoch_seed())
         H, W = self.cache.src_hw
         q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)
         free: "queue.Queue" = queue.Queue()

@@ -233,3 +233,35 @@ def test_native_png_decoder_matches_pil(synth_root, tmp_path):
     f4 = str(tmp_path / "pal4.png")
     Image.fromarray(base[..., :3], "RGB").quantize(16).save(f4)      # 4-bit palette: not handled natively
     assert ops.native_decode_pngs([f4], 1) is None                   # -> caller falls back to PIL
+
+
+def test_native_prefetcher_matches_python_loader(synth_root):
+    """csrc/prefetch.cpp worker: same batches (images, labels, sizes) as the Python producer thread;
+    transform parameters follow torchvision's ranges."""
+    from distributed_vgg_f_b200 import ops
+    from distributed_vgg_f_b200.data.loader import DataManager
+
+    if not ops.available():
+        pytest.skip("native extension not built")
+    dm = DataManager(synth_root, 5, train=True, seed=3)
+    ld = dm.get_loader()
+    assert ld._pf is not None
+    ld.set_epoch(1)
+    nat = [(b.images_u8.clone(), b.labels.clone(), b.params.clone()) for b in ld]
+    ld._pf, keep = None, ld._pf
+    ld.set_epoch(1)
+    py = [(b.images_u8.clone(), b.labels.clone(), b.params.clone()) for b in ld]
+    ld._pf = keep
+    assert [len(a[1]) for a in nat] == [5, 5, 5, 5, 4] == [len(a[1]) for a in py]
+    for a, b in zip(nat, py):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    p = torch.cat([a[2] for a in nat])
+    area = p[:, 2] * p[:, 3] / (128 * 128)
+    assert float(area.min()) > 0.75 and float(area.max()) <= 1.0
+    assert bool(((p[:, 0] + p[:, 2]) <= 128).all() and ((p[:, 1] + p[:, 3]) <= 128).all())
+    assert float(torch.atan2(p[:, 5], p[:, 4]).abs().max()) <= math.radians(10.0) + 1e-5
+    # two epochs in a row and an abandoned iteration must not dead-lock the worker
+    it = iter(ld)
+    next(it)
+    del it
+    assert sum(len(b.labels) for b in ld) == 24
