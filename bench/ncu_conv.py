@@ -22,3 +22,13 @@ def run(h, cin, cout, what):
 run(224, 64, 64, "fdw")
 run(56, 256, 256, "fdw")
 run(28, 512, 512, "f")
+run(14, 512, 512, "f")
+# first conv (fused, no im2col)
+x4 = torch.randn(B, 224, 224, 4, device=dev).bfloat16()
+w0 = torch.randn(64, 64, device=dev).bfloat16()
+y0 = torch.empty(B, 224, 224, 64, dtype=torch.bfloat16, device=dev)
+dw0 = torch.zeros(64, 64, device=dev)
+for _ in range(2):
+    C.conv0_fprop(x4, w0, torch.zeros(64, device=dev), y0)
+    C.conv0_wgrad(y0, x4, dw0)
+torch.cuda.synchronize()
