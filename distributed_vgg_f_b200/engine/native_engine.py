@@ -46,20 +46,25 @@ def _round_up(x: int, m: int) -> int:
 class PhaseTimer:
     """CUDA-event timers around the phases of a step (``--profile events``)."""
 
-    def __init__(self, enabled: bool) -> None:
+    def __init__(self, enabled: bool, nvtx: bool = False) -> None:
         self.enabled = enabled
+        self.nvtx = nvtx
         self.pending: List[Tuple[str, torch.cuda.Event, torch.cuda.Event]] = []
         self.totals: Dict[str, float] = {}
         self.counts: Dict[str, int] = {}
         self._open: Dict[str, torch.cuda.Event] = {}
 
     def start(self, name: str) -> None:
+        if self.nvtx:
+            torch.cuda.nvtx.range_push(name)
         if self.enabled:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
             self._open[name] = e
 
     def stop(self, name: str) -> None:
+        if self.nvtx:
+            torch.cuda.nvtx.range_pop()
         if self.enabled and name in self._open:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
@@ -100,7 +105,7 @@ class NativeEngine:
         self.apply_updates = True        # False: leave raw gradients in g32 (gradient inspection)
         self.meter: Optional[DeviceMeter] = None
         self.class_weights: Optional[torch.Tensor] = None
-        self.timer = PhaseTimer(profile == "events")
+        self.timer = PhaseTimer(profile == "events", nvtx=(profile == "nvtx"))
         self.nvtx = profile == "nvtx"
         self.world = dist.get_world_size() if (distributed and distributed_is_initialized()) else 1
         self.rank = dist.get_rank() if (distributed and distributed_is_initialized()) else 0
