@@ -123,6 +123,8 @@ static ConvTile make_tile(int N, int H, int W, int pixels) {
   t.tiles_h = (H + t.Hb - 1) / t.Hb;
   t.wb_shift = 0; while ((1 << t.wb_shift) < t.Wb) ++t.wb_shift;
   t.hb_shift = 0; while ((1 << t.hb_shift) < t.Hb) ++t.hb_shift;
+  t.div_tw = make_fastdiv(t.tiles_w);
+  t.div_th = make_fastdiv(t.tiles_h);
   return t;
 }
 
@@ -148,7 +150,9 @@ static void conv_halo_launch(ConvParams& prm, const bf16* act, cudaStream_t stre
   ConvTile& t = prm.t;
   t.Wb = HALO_WT; t.Hb = HALO_HT; t.Nb = 1; t.wb_shift = 3; t.hb_shift = 4;
   t.tiles_w = t.W / HALO_WT; t.tiles_h = t.H / HALO_HT;
+  t.div_tw = make_fastdiv(t.tiles_w); t.div_th = make_fastdiv(t.tiles_h);
   prm.tiles_m = t.tiles_w * t.tiles_h * t.N;
+  prm.div_tm = make_fastdiv(prm.tiles_m);
   const int tiles_n = (prm.Cn + BN - 1) / BN;
   prm.num_tiles = prm.tiles_m * tiles_n;
   prm.resident = (tiles_n == 1 && 9 * (prm.Ca / UMMA_BK) <= Cfg::NB) ? 1 : 0;
@@ -275,6 +279,7 @@ static void conv_launch(ConvParams& prm, cudaStream_t stream) {
   const ConvTile& t = prm.t;
   const int tiles_n = (t.N + t.Nb - 1) / t.Nb;
   prm.tiles_m = t.tiles_w * t.tiles_h * tiles_n;
+  prm.div_tm = make_fastdiv(prm.tiles_m);
   prm.num_tiles = prm.tiles_m * ((prm.Cn + BN - 1) / BN);
   launch<P>(prm, stream);
 }
