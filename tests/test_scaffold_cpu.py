@@ -265,3 +265,57 @@ def test_native_prefetcher_matches_python_loader(synth_root):
     next(it)
     del it
     assert sum(len(b.labels) for b in ld) == 24
+
+
+def test_native_layout_roundtrip_and_semantics():
+    """models.layout: torch <-> native conversions are inverse, and the native layouts mean what the
+    kernels assume (OHWI conv weights, im2col-ordered first conv, NHWC-ordered classifier.0 columns)."""
+    from distributed_vgg_f_b200.models import layout as L
+    from distributed_vgg_f_b200.models.vggf import vggf_mini_spec
+
+    spec = vggf_mini_spec(3)
+    torch.manual_seed(0)
+    for name in spec.param_names:
+        t = torch.randn(spec.param_shape(name))
+        n = L.to_native(spec, name, t)
+        assert tuple(n.shape) == L.native_shape(spec, name), name
+        assert torch.equal(L.to_torch(spec, name, n), t), name
+    # first conv: y = im2col(x) @ W0^T with k = (kh*3+kw)*3 + c
+    w = torch.randn(64, 3, 3, 3)
+    x = torch.randn(1, 3, 6, 6)
+    w0 = L.to_native(spec, "features.0.weight", w)
+    cols = torch.nn.functional.unfold(x, 3, padding=1).view(1, 3, 9, 36).permute(0, 3, 2, 1).reshape(36, 27)
+    got = (cols @ w0[:, :27].t()).t().reshape(1, 64, 6, 6)
+    assert torch.allclose(got, torch.nn.functional.conv2d(x, w, padding=1), atol=1e-4)
+    assert torch.count_nonzero(w0[:, 27:]) == 0
+    # classifier.0: NHWC flatten of the feature map times the permuted weight == NCHW flatten times the original
+    f = spec.fcs[0]
+    wfc = torch.randn(f.fout, f.fin)
+    feat = torch.randn(2, f.fin // 49, 7, 7)
+    a = torch.flatten(feat, 1) @ wfc.t()
+    b = feat.permute(0, 2, 3, 1).reshape(2, -1) @ L.to_native(spec, f.name + ".weight", wfc).t()
+    assert torch.allclose(a, b, atol=1e-3)
+
+
+def test_emulated_reference_tracks_autograd():
+    """ops.ref.emulated_step (the engine's oracle: torch fp32 ops with the engine's bf16 rounding
+    points) stays close to plain autograd on a small network."""
+    import torch.nn.functional as F
+
+    from distributed_vgg_f_b200.models.vggf import vggf_tiny_spec
+    from distributed_vgg_f_b200.ops import ref as R
+
+    spec = vggf_tiny_spec(3)
+    model = build_oracle(spec, seed=0).eval()
+    torch.manual_seed(1)
+    x = torch.randn(2, 3, 32, 32)
+    y = torch.tensor([0, 2])
+    loss = F.cross_entropy(model(x), y)
+    loss.backward()
+    state = {k: v.detach() for k, v in model.state_dict().items()}
+    logits, eloss, grads = R.emulated_step(spec, state, x, y)
+    assert abs(float(eloss) - float(loss)) < 5e-2
+    for name, p in model.named_parameters():
+        a, b = grads[name].flatten(), p.grad.flatten()
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+        assert cos > 0.9, (name, cos)       # bf16 rounding drift grows towards the input layers
