@@ -351,12 +351,28 @@ void fc_bias_act(float* acc, const float* bias, bf16* y, float* y_f32, int B, in
 __global__ void fc_grad_act_kernel(float* __restrict__ acc, const bf16* __restrict__ act,
                                    bf16* __restrict__ dz, long long total, int relu, float scale,
                                    int clear) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+  const long long n4 = total / 4;       // 16-byte fp32 / 8-byte bf16 vectors
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float v = acc[i];
-    if (clear) acc[i] = 0.f;
-    if (relu) v = __bfloat162float(act[i]) > 0.f ? v * scale : 0.f;
-    dz[i] = __float2bfloat16(v);
+    float4 v = reinterpret_cast<float4*>(acc)[i];
+    if (clear) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (relu) {
+      const uint2 a = *reinterpret_cast<const uint2*>(act + i * 4);
+      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y);
+      v.x = a0.x > 0.f ? v.x * scale : 0.f;
+      v.y = a0.y > 0.f ? v.y * scale : 0.f;
+      v.z = a1.x > 0.f ? v.z * scale : 0.f;
+      v.w = a1.y > 0.f ? v.w * scale : 0.f;
+    }
+    *reinterpret_cast<uint2*>(dz + i * 4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+  if (blockIdx.x == 0) {                // scalar tail
+    for (long long i = n4 * 4 + threadIdx.x; i < total; i += blockDim.x) {
+      float v = acc[i];
+      if (clear) acc[i] = 0.f;
+      if (relu) v = __bfloat162float(act[i]) > 0.f ? v * scale : 0.f;
+      dz[i] = __float2bfloat16(v);
+    }
   }
 }
 
@@ -364,8 +380,11 @@ void fc_grad_act(float* acc, const bf16* act, bf16* dz, int B, int N, bool relu,
                  unsigned long long, unsigned long long, bool clear, cudaStream_t s) {
   const long long total = static_cast<long long>(B) * N;
   const float scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  fc_grad_act_kernel<<<min(ceil_div_ll(total, 256), 148 * 8), 256, 0, s>>>(acc, act, dz, total,
-                                                                           relu ? 1 : 0, scale, clear ? 1 : 0);
+  if ((reinterpret_cast<uintptr_t>(acc) & 15) || (reinterpret_cast<uintptr_t>(dz) & 7) ||
+      (act && (reinterpret_cast<uintptr_t>(act) & 7)))
+    throw std::runtime_error("[b200] fc_grad_act: buffers must be 16-byte (fp32) / 8-byte (bf16) aligned");
+  fc_grad_act_kernel<<<min(ceil_div_ll(total / 4 + 1, 256), 148 * 8), 256, 0, s>>>(acc, act, dz, total,
+                                                                                   relu ? 1 : 0, scale, clear ? 1 : 0);
   count_launch();
   check_last("fc_grad_act");
 }
