@@ -20,6 +20,8 @@ Nothing synchronises with the host inside a step; loss / accuracy accumulate in 
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Dict, List, Optional, Tuple
 
@@ -129,12 +131,29 @@ class NativeEngine:
 
         # ---- cross-GPU plumbing ------------------------------------------------------------------
         self.arena = None
+        self.cross_group = None          # inter-node stage of the hierarchical reduction
+        self.comm_mode = "single" if self.world == 1 else ("nccl" if self.use_nccl else "flat")
         self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)
         if self.world > 1 and not self.use_nccl:
+            from ..parallel import topology
             from ..parallel.symm import SymmetricArena
 
-            wdt = BF16 if wire_dtype == "bf16" else F32
-            self.arena = SymmetricArena(n, dev, wire_dtype=wdt)
+            layout = topology.detect_layout()
+            self.comm_mode = layout.mode()
+            if self.comm_mode == "flat" and os.environ.get("B200_FORCE_HIERARCHICAL", "0") == "1":
+                self.comm_mode = "hierarchical"          # test hook: one node, both stages exercised
+            node_group = None
+            if self.comm_mode == "hierarchical":
+                node_group, self.cross_group = topology.make_hierarchy_groups(layout)
+            if self.comm_mode == "nccl":
+                # one GPU per host (the reference's deployment) or uneven hosts: no peer memory to fuse over
+                self.use_nccl = True
+                if self.rank == 0:
+                    print(f"[b200] {layout.n_nodes} hosts x {layout.local_size} GPU: gradient all-reduce "
+                          f"falls back to NCCL (--allreduce {allreduce} needs an NVLink domain)", flush=True)
+            else:
+                wdt = BF16 if wire_dtype == "bf16" else F32
+                self.arena = SymmetricArena(n, dev, wire_dtype=wdt, group=node_group)
         if self.world > 1:
             self._broadcast_params()
         # buckets holding only FC weight gradients are written with plain stores by the wgrad GEMM:
@@ -197,7 +216,7 @@ class NativeEngine:
 
     def _broadcast_params(self) -> None:
         """DDP's constructor sync (distributedVggf.py:225): everybody adopts rank 0's weights."""
-        if self.arena is not None:
+        if self.arena is not None and self.cross_group is None:
             self.arena.broadcast_(self.p32, root=0)
         else:
             dist.broadcast(self.p32, src=0)
@@ -494,7 +513,10 @@ class NativeEngine:
             to_f32 = (algo == "oneshot" or self.unpack_fp32 or self.arena.wire_dtype == F32
                       or not self.apply_updates)
             self.arena.allreduce(None if prepacked else self.g32, self.g32 if to_f32 else None, s, e - s,
-                                 algo=algo, slot=bi % self.arena.slots, max_ctas=self.comm_ctas)
+                                 algo=algo, slot=bi % self.arena.slots, max_ctas=self.comm_ctas,
+                                 inv_world=1.0 / self.world)
+            if self.cross_group is not None:     # node sums (already x 1/world) -> job sum, over NCCL
+                dist.all_reduce(self.g32[s:e] if to_f32 else self.arena.wire[s:e], group=self.cross_group)
             if self.apply_updates:
                 self._apply_update(s, e, None if to_f32 else self.arena.wire[s:e],
                                    zero=not (prepacked or self._bucket_store_only[bi]))

@@ -118,3 +118,45 @@ def _grad_worker(rank, world, port):
     for (n, a), (_, b) in zip(ddp.module.named_parameters(), single.named_parameters()):
         assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-6), n
     dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------- node topology
+def test_node_layout_modes():
+    from distributed_vgg_f_b200.parallel.topology import layout_from_ids
+
+    one = layout_from_ids(["a"] * 8, rank=5)
+    assert (one.n_nodes, one.local_size, one.local_rank, one.mode()) == (1, 8, 5, "flat")
+    two = layout_from_ids(["a", "a", "b", "b"], rank=3)
+    assert (two.n_nodes, two.node, two.local_rank, two.local_size, two.mode()) == (2, 1, 1, 2, "hierarchical")
+    assert two.members(0) == [0, 1] and two.members(1) == [2, 3]
+    interleaved = layout_from_ids(["a", "b", "a", "b"], rank=2)     # rank order need not follow hosts
+    assert interleaved.members(0) == [0, 2] and interleaved.local_rank == 1
+    vms = layout_from_ids(["vm0", "vm1", "vm2"], rank=1)             # the reference: one GPU per VM
+    assert vms.mode() == "nccl"
+    uneven = layout_from_ids(["a", "a", "b"], rank=0)
+    assert not uneven.uniform and uneven.mode() == "nccl"
+
+
+def _topology_worker(rank, world, port):
+    import torch.distributed as dist
+
+    from distributed_vgg_f_b200.parallel import topology
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    assert topology.detect_layout().mode() == "flat"                 # same host
+    os.environ["B200_FAKE_NODE_SIZE"] = "2"
+    layout = topology.detect_layout()
+    assert (layout.n_nodes, layout.local_size, layout.mode()) == (2, 2, "hierarchical")
+    node_group, cross_group = topology.make_hierarchy_groups(layout)
+    # two-stage sum == flat sum
+    x = torch.full((5,), float(rank + 1))
+    dist.all_reduce(x, group=node_group)
+    dist.all_reduce(x, group=cross_group)
+    assert torch.equal(x, torch.full((5,), 10.0)), x
+    dist.destroy_process_group()
+
+
+def test_hierarchy_groups_gloo_world4():
+    import torch.multiprocessing as mp
+
+    mp.spawn(_topology_worker, args=(4, _free_port()), nprocs=4, join=True)

@@ -85,7 +85,7 @@ def test_fused_allreduce_matches_nccl(wire_fp32):
 
 
 # ---------------------------------------------------------------------------------- engine DDP
-def _engine_worker(rank, world, algo):
+def _engine_worker(rank, world, algo, expect_mode="flat"):
     from distributed_vgg_f_b200.engine.native_engine import NativeEngine
     from distributed_vgg_f_b200.models.vggf import build_oracle, vggf_mini_spec
 
@@ -99,6 +99,7 @@ def _engine_worker(rank, world, algo):
     single = NativeEngine(spec, device=dev, batch=4 * world, lr=1e-3, seed=0, input_hw=64, init_state=ref_init,
                           distributed=False)
     assert torch.equal(eng.p32, single.p32), "rank-0 weights were not broadcast"
+    assert eng.comm_mode == expect_mode, eng.comm_mode
     for e in (eng, single):
         e.train_dropout = False
         e.apply_updates = False
@@ -125,6 +126,36 @@ def _engine_worker(rank, world, algo):
 @pytest.mark.parametrize("algo", ["auto", "twoshot", "oneshot"])
 def test_engine_data_parallel_equivalence(algo):
     _run(_engine_worker, 2, algo)
+
+
+def _hier_worker(rank, world, fake_node_size):
+    if fake_node_size:
+        os.environ["B200_FAKE_NODE_SIZE"] = str(fake_node_size)
+    else:
+        os.environ["B200_FORCE_HIERARCHICAL"] = "1"
+    _engine_worker(rank, world, "auto", expect_mode="hierarchical")
+
+
+def test_engine_hierarchical_reduction_one_node():
+    """Both stages of the multi-node path (node-group fused all-reduce scaled by 1/world, then the
+    cross-node NCCL all-reduce) on a single host: node group = all ranks, cross groups of size 1."""
+    _run(_hier_worker, 2, 0)
+
+
+def test_engine_hierarchical_reduction_fake_nodes():
+    """4 GPUs posing as 2 hosts x 2 GPUs."""
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    _run(_hier_worker, 4, 2)
+
+
+def _fallback_worker(rank, world):
+    os.environ["B200_FAKE_NODE_SIZE"] = "1"          # the reference's deployment: one GPU per host
+    _engine_worker(rank, world, "auto", expect_mode="nccl")
+
+
+def test_engine_one_gpu_per_host_falls_back_to_nccl():
+    _run(_fallback_worker, 2)
 
 
 # ------------------------------------------------------------------------- barrier stress test
