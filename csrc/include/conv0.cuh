@@ -190,12 +190,15 @@ __global__ void __launch_bounds__(C0_THREADS, 1) conv0_kernel(const __grid_const
         if (pix < prm.pixels) {
           __nv_bfloat16* o = prm.out + static_cast<long long>(pix) * 64 + c;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float v[8];
+          for (int j = 0; j < 32; j += 16) {     // 64 contiguous bytes per thread: two 32-byte stores
+            uint32_t pk[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = fmaxf(__uint_as_float(acc[j + u]) + __ldg(prm.bias + c + j + u), 0.f);
-            *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                          pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            for (int u = 0; u < 8; ++u) {
+              const float lo = fmaxf(__uint_as_float(acc[j + 2 * u]) + __ldg(prm.bias + c + j + 2 * u), 0.f);
+              const float hi = fmaxf(__uint_as_float(acc[j + 2 * u + 1]) + __ldg(prm.bias + c + j + 2 * u + 1), 0.f);
+              pk[u] = pack_bf16x2(lo, hi);
+            }
+            st_global_v8(o + j, pk);
           }
         }
         tc_fence_before_sync();

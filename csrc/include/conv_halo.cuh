@@ -83,27 +83,27 @@ conv_halo_kernel(const __grid_constant__ ConvParams prm) {
 
   // Converged producer / MMA warps with elect.sync-predicated issue (see umma_core.cuh).
   if (warp == 0) {
-    uint32_t ait = 0, bit = 0;
+    uint32_t a = 0, aph = 0, bs = 0, bph = 0;      // ring positions / phases as counters
     bool first = true;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const typename Epi::Ctx ctx = Epi::make_ctx(prm, tile);
-      for (int c = 0; c < cchunks; ++c, ++ait) {
-        const uint32_t a = ait % NA;
-        mbar_wait(&a_empty[a], ((ait / NA) & 1) ^ 1, 21);
+      for (int c = 0; c < cchunks; ++c) {
+        mbar_wait(&a_empty[a], aph ^ 1, 21);
         if (elect_one()) {
           mbar_arrive_expect_tx(&a_full[a], HALO_BYTES);
           tma_load_4d(sA + a * HALO_SLOT, &prm.mapA, &a_full[a], c * UMMA_BK, ctx.w0 - 1, ctx.h0 - 1, ctx.n0);
         }
         __syncwarp();
+        if (++a == NA) { a = 0; aph ^= 1; }
         if (resident && !first) continue;
         for (int tap = 0; tap < 9; ++tap) {
           uint32_t b;
           if (resident) {
             b = c * 9 + tap;
           } else {
-            b = bit % NB;
-            mbar_wait(&b_empty[b], ((bit / NB) & 1) ^ 1, 22);
-            ++bit;
+            b = bs;
+            mbar_wait(&b_empty[b], bph ^ 1, 22);
+            if (++bs == NB) { bs = 0; bph ^= 1; }
           }
           if (elect_one()) {
             mbar_arrive_expect_tx(&b_full[b], B_SLOT);
@@ -127,43 +127,69 @@ conv_halo_kernel(const __grid_constant__ ConvParams prm) {
     constexpr uint32_t idesc = umma_idesc_bf16(UMMA_BM, BN, false, DGRAD);
     constexpr uint32_t B_KSTEP = DGRAD ? 16 * 128 : 32;
     constexpr uint32_t B_LBO = DGRAD ? UMMA_SLAB_BYTES : 16;
-    uint32_t ait = 0, bit = 0, t = 0;
+    // The MMA warp has to keep up with N=64 MMAs of 32 tensor cycles each, so its loops carry no
+    // address arithmetic: every descriptor is a base plus a compile-time constant (the address
+    // field is addr >> 4 and shared memory is < 256 KB: the add cannot carry out of the field),
+    // the nine taps are unrolled, ring positions are counters.  (The first version rebuilt both
+    // descriptors per tap in a rolled loop: ~300 issue cycles per tap against 128 of tensor time;
+    // the 64-channel layers ran at 25-32 % tensor-pipe active.)
+    const uint64_t ad_base = umma_smem_desc_sw128(smem_u32(sA), 16, HALO_PITCH * 128);
+    const uint64_t bd_base = umma_smem_desc_sw128(smem_u32(sB), B_LBO, 1024);
+    uint32_t a = 0, aph = 0, bs = 0, bph = 0, t = 0;
     bool first = true;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const uint32_t buf = t & 1;
       mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1, 24);
       tc_fence_after_sync();
       const uint32_t tmem_acc = tmem_base + buf * BN;
-      for (int c = 0; c < cchunks; ++c, ++ait) {
-        const uint32_t a = ait % NA;
-        mbar_wait(&a_full[a], (ait / NA) & 1, 25);
+      for (int c = 0; c < cchunks; ++c) {
+        mbar_wait(&a_full[a], aph, 25);
         tc_fence_after_sync();
-        const uint32_t a0 = smem_u32(sA + a * HALO_SLOT);
-        for (int tap = 0; tap < 9; ++tap) {
-          uint32_t b;
-          if (resident) {
-            b = c * 9 + tap;
-            if (first) mbar_wait(&b_full[b], 0, 26);
-          } else {
-            b = bit % NB;
-            mbar_wait(&b_full[b], (bit / NB) & 1, 27);
-            ++bit;
-          }
-          tc_fence_after_sync();
-          // tap view of the halo: starts kh rows of 10 pixels + kw pixels in, 10-pixel group pitch
-          const uint64_t ad0 = umma_smem_desc_sw128(a0 + ((tap / 3) * HALO_PITCH + tap % 3) * 128, 16,
-                                                    HALO_PITCH * 128);
-          const uint64_t bd0 = umma_smem_desc_sw128(smem_u32(sB + b * B_SLOT), B_LBO, 1024);
+        const uint64_t ad = ad_base + a * (HALO_SLOT >> 4);
+        const uint32_t acc_c = c != 0 ? 1u : 0u;
+        if (resident && !first) {
+          // steady state, resident weights: nothing to wait for between taps -- 36 MMAs back to back
+          const uint64_t bd = bd_base + c * (9 * B_SLOT >> 4);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < UMMA_BK / 16; ++k)
-              umma_f16(tmem_acc, ad0 + k * 2, bd0 + k * (B_KSTEP >> 4), idesc, (c | tap | k) != 0 ? 1u : 0u);
-            if (!resident) umma_commit(&b_empty[b]);
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+              for (int k = 0; k < UMMA_BK / 16; ++k)
+                umma_f16(tmem_acc, ad + (((tap / 3) * HALO_PITCH + tap % 3) * 128 >> 4) + k * 2,
+                         bd + (tap * B_SLOT >> 4) + k * (B_KSTEP >> 4), idesc,
+                         (tap | k) != 0 ? 1u : acc_c);
+            }
+            umma_commit(&a_empty[a]);
           }
           __syncwarp();
+        } else {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t b;
+            if (resident) {          // first tile of this CTA: the weights are still arriving
+              b = c * 9 + tap;
+              mbar_wait(&b_full[b], 0, 26);
+            } else {
+              b = bs;
+              mbar_wait(&b_full[b], bph, 27);
+              if (++bs == NB) { bs = 0; bph ^= 1; }
+            }
+            tc_fence_after_sync();
+            // tap view of the halo: starts kh rows of 10 pixels + kw pixels in, 10-pixel group pitch
+            const uint64_t bd = bd_base + b * (B_SLOT >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < UMMA_BK / 16; ++k)
+                umma_f16(tmem_acc, ad + (((tap / 3) * HALO_PITCH + tap % 3) * 128 >> 4) + k * 2,
+                         bd + k * (B_KSTEP >> 4), idesc, (tap | k) != 0 ? 1u : acc_c);
+              if (!resident) umma_commit(&b_empty[b]);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit(&a_empty[a]);
+          __syncwarp();
         }
-        if (elect_one()) umma_commit(&a_empty[a]);
-        __syncwarp();
+        if (++a == NA) { a = 0; aph ^= 1; }
       }
       first = false;
       if (elect_one()) umma_commit(&acc_full[buf]);
@@ -182,15 +208,36 @@ conv_halo_kernel(const __grid_constant__ ConvParams prm) {
       const typename Epi::Ctx ctx = Epi::make_ctx(prm, tile);
       const typename Epi::RowCtx rc = Epi::row_ctx(prm, ctx, row);
       const uint32_t buf = t & 1;
-      mbar_wait(&acc_full[buf], (t >> 1) & 1, 28);
-      tc_fence_after_sync();
       uint32_t acc[32];
+      if constexpr (DGRAD) {
+        // dgrad: fetch the ReLU masks of this warp's chunks before waiting for the accumulator
+        constexpr int NCH = BN / 64;
+        uint32_t mk[NCH][16];
+        const bool masked = (prm.flags & CONV_MASK) != 0;
+        if (masked) {
+#pragma unroll
+          for (int ci = 0; ci < NCH; ++ci) Epi::load_mask(prm, ctx, rc, half * 32 + ci * 64, mk[ci]);
+        }
+        mbar_wait(&acc_full[buf], (t >> 1) & 1, 28);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = half * 32 + ci * 64;
+          __syncwarp();
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c, acc);
+          tmem_ld_wait();
+          Epi::epilogue(prm, ctx, rc, row, c, acc, epi_smem, masked ? mk[ci] : nullptr);
+        }
+      } else {
+        mbar_wait(&acc_full[buf], (t >> 1) & 1, 28);
+        tc_fence_after_sync();
 #pragma unroll 1
-      for (int c = half * 32; c < BN; c += 64) {
-        __syncwarp();
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c, acc);
-        tmem_ld_wait();
-        Epi::epilogue(prm, ctx, rc, row, c, acc, epi_smem);
+        for (int c = half * 32; c < BN; c += 64) {
+          __syncwarp();
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c, acc);
+          tmem_ld_wait();
+          Epi::epilogue(prm, ctx, rc, row, c, acc, epi_smem);
+        }
       }
       tc_fence_before_sync();
       __syncwarp();

@@ -285,6 +285,21 @@ __device__ __forceinline__ void multimem_red_add_u32(uint32_t* mc_ptr, uint32_t 
 }
 
 // ------------------------------------------------------------------------------- bf16 helpers
+// 256-bit global accesses (sm_100: LDG.256 / STG.256).  An epilogue thread owns 64 contiguous bytes
+// of one pixel while its neighbours own other pixels, so every warp-wide access touches 32 cache
+// lines whatever its width: two 32-byte accesses cost half the L1 wavefronts of four 16-byte ones.
+// The address must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t* v) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -110,19 +110,18 @@ umma_kernel(const __grid_constant__ typename P::Params prm) {
   // descriptors are then warp-uniform values the compiler keeps in uniform registers, instead of
   // per-lane values that need a waterfall loop around every UTCHMMA / UTMALDG.
   if (warp == 0) {
-    uint32_t it = 0;
+    uint32_t s = 0, ph = 0;                 // ring position / phase kept as counters (no div/mod)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const typename P::Ctx ctx = P::make_ctx(prm, tile);
       const int nk = P::num_k_iters(prm, ctx);
-      for (int i = 0; i < nk; ++i, ++it) {
-        const uint32_t s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
+      for (int i = 0; i < nk; ++i) {
         mbar_wait(&empty_bar[s], ph ^ 1, 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[s], STAGE_TX);
           P::load(prm, ctx, i, sA + s * UMMA_A_BYTES, sB + s * B_BYTES, &full_bar[s]);
         }
         __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -132,7 +131,11 @@ umma_kernel(const __grid_constant__ typename P::Params prm) {
     constexpr uint32_t B_KSTEP = P::B_MN ? 16 * 128 : 32;
     constexpr uint32_t A_LBO = P::A_MN ? UMMA_SLAB_BYTES : 16;
     constexpr uint32_t B_LBO = P::B_MN ? UMMA_SLAB_BYTES : 16;
-    uint32_t it = 0, t = 0;
+    uint32_t s = 0, ph = 0, t = 0;
+    // Stage descriptors are base + s * stage size: the address field is addr >> 4 and shared
+    // memory is < 256 KB, so the add never carries out of the 14-bit field.
+    const uint64_t ad_base = umma_smem_desc_sw128(smem_u32(sA), A_LBO, 1024);
+    const uint64_t bd_base = umma_smem_desc_sw128(smem_u32(sB), B_LBO, 1024);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const typename P::Ctx ctx = P::make_ctx(prm, tile);
       const int nk = P::num_k_iters(prm, ctx);
@@ -140,13 +143,11 @@ umma_kernel(const __grid_constant__ typename P::Params prm) {
       mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1, 4);     // epilogue drained this buffer
       tc_fence_after_sync();
       const uint32_t tmem_acc = tmem_base + buf * BN;
-      for (int i = 0; i < nk; ++i, ++it) {
-        const uint32_t s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
+      for (int i = 0; i < nk; ++i) {
         mbar_wait(&full_bar[s], ph, 2);
         tc_fence_after_sync();
-        const uint64_t ad0 = umma_smem_desc_sw128(smem_u32(sA + s * UMMA_A_BYTES), A_LBO, 1024);
-        const uint64_t bd0 = umma_smem_desc_sw128(smem_u32(sB + s * B_BYTES), B_LBO, 1024);
+        const uint64_t ad0 = ad_base + s * (UMMA_A_BYTES >> 4);
+        const uint64_t bd0 = bd_base + s * (B_BYTES >> 4);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < UMMA_BK / 16; ++k)     // start-address field is in 16-byte units
@@ -154,6 +155,7 @@ umma_kernel(const __grid_constant__ typename P::Params prm) {
           umma_commit(&empty_bar[s]);       // frees the smem stage when these MMAs retire
         }
         __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       if (elect_one()) umma_commit(&acc_full[buf]);        // accumulator of this tile complete
       __syncwarp();

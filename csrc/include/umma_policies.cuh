@@ -310,8 +310,24 @@ struct ConvPolicy {
     }
   }
 
+  // The ReLU mask of a dgrad chunk (the previous layer's activations at this thread's pixel)
+  // depends only on the tile, not on the accumulator: kernels whose epilogue is on the critical
+  // path fetch it BEFORE they wait for the MMAs, so the global-load latency is off that path.
+  __device__ static void load_mask(const Params& p, const Ctx& c, const RowCtx& rc, int col0, uint32_t (&m)[16]) {
+    const int ch = c.c0 + col0;
+    if (rc.valid && ch < p.Cn) {
+      const __nv_bfloat16* src = p.mask_src + rc.pix_off + ch;
+      ld_global_nc_v8(src, m);
+      ld_global_nc_v8(src + 16, m + 8);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) m[j] = 0u;
+    }
+  }
+
+  // One 32-column chunk of one pixel: 64 contiguous bytes, written as two 32-byte stores.
   __device__ static void epilogue(const Params& p, const Ctx& c, const RowCtx& rc, int row, int col0,
-                                  const uint32_t (&acc)[32], float* sm) {
+                                  const uint32_t (&acc)[32], float* sm, const uint32_t* premask = nullptr) {
     const int ch = c.c0 + col0;
     const bool valid = rc.valid && ch < p.Cn;
     const long long off = rc.pix_off + ch;
@@ -320,46 +336,52 @@ struct ConvPolicy {
     const int lane = row & 31;
     float cs[32];                                           // what this thread stored (bf16-rounded)
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      float v[8];
+    for (int j = 0; j < 32; j += 16) {
+      float v[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(acc[j + u]);
+      for (int u = 0; u < 16; ++u) v[u] = __uint_as_float(acc[j + u]);
       if (valid) {
         if (!DGRAD && (p.flags & CONV_BIAS)) {
-          const float4 b0 = *reinterpret_cast<const float4*>(sm + ch + j);     // smem broadcast
-          const float4 b1 = *reinterpret_cast<const float4*>(sm + ch + j + 4);
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+#pragma unroll
+          for (int u = 0; u < 16; u += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(sm + ch + j + u);     // smem broadcast
+            v[u] += b.x; v[u + 1] += b.y; v[u + 2] += b.z; v[u + 3] += b.w;
+          }
         }
         if (p.flags & CONV_RELU) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
+          for (int u = 0; u < 16; ++u) v[u] = fmaxf(v[u], 0.f);
         }
         if (p.flags & CONV_MASK) {
-          const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask_src + off + j));
-          const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+          uint32_t mw[8];
+          if (premask) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) mw[u] = premask[(j >> 1) + u];
+          } else {
+            ld_global_nc_v8(p.mask_src + off + j, mw);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
             const float2 f = unpack_bf16x2(mw[u]);
             if (!(f.x > 0.f)) v[2 * u] = 0.f;
             if (!(f.y > 0.f)) v[2 * u + 1] = 0.f;
           }
         }
-        const uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                    pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        *reinterpret_cast<uint4*>(o + j) = pk;
-        if (colsum) {        // sum exactly what was stored, like a separate pass over dz would
-          const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+        uint32_t pk[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float2 f = unpack_bf16x2(pw[u]);
+        for (int u = 0; u < 8; ++u) pk[u] = pack_bf16x2(v[2 * u], v[2 * u + 1]);
+        st_global_v8(o + j, pk);
+        if (colsum) {        // sum exactly what was stored, like a separate pass over dz would
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float2 f = unpack_bf16x2(pk[u]);
             cs[j + 2 * u] = f.x;
             cs[j + 2 * u + 1] = f.y;
           }
         }
       } else if (colsum) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) cs[j + u] = 0.f;
+        for (int u = 0; u < 16; ++u) cs[j + u] = 0.f;
       }
     }
     if (colsum) {
