@@ -204,6 +204,13 @@ conv_halo_kernel(const __grid_constant__ ConvParams prm) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     uint32_t t = 0;
+    // Fused bias gradient with a single channel tile (the 64-channel layers): every tile of this
+    // CTA lands on the same columns, so a thread keeps running sums of what it stored and the
+    // warp transpose-reduce runs once per kernel instead of once per tile.
+    float keep[32];
+    const bool keep_on = DGRAD && BN == 64 && (prm.flags & CONV_COLSUM) && prm.Cn <= BN;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) keep[i] = 0.f;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const typename Epi::Ctx ctx = Epi::make_ctx(prm, tile);
       const typename Epi::RowCtx rc = Epi::row_ctx(prm, ctx, row);
@@ -226,7 +233,7 @@ conv_halo_kernel(const __grid_constant__ ConvParams prm) {
           __syncwarp();
           tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c, acc);
           tmem_ld_wait();
-          Epi::epilogue(prm, ctx, rc, row, c, acc, epi_smem, masked ? mk[ci] : nullptr);
+          Epi::epilogue(prm, ctx, rc, row, c, acc, epi_smem, masked ? mk[ci] : nullptr, keep, keep_on);
         }
       } else {
         mbar_wait(&acc_full[buf], (t >> 1) & 1, 28);
@@ -242,6 +249,9 @@ conv_halo_kernel(const __grid_constant__ ConvParams prm) {
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    if constexpr (DGRAD) {
+      if (keep_on) Epi::colsum_flush(prm, half * 32, lane, keep, epi_smem);
     }
     if constexpr (Epi::EPI_SMEM > 0) {
       asm volatile("bar.sync 1, 256;" ::: "memory");

@@ -125,7 +125,16 @@ struct GemmPolicy {
     if constexpr (EPI == EPI_F32_STORE || EPI == EPI_F32_ATOMIC) {
       float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(r) * p.ldo + cb;
       const bool vec = (cb + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
-      if (vec) {
+      if (EPI == EPI_F32_STORE && vec && (reinterpret_cast<uintptr_t>(o) & 31) == 0) {
+        // a thread owns one 128-byte line of the output: four full-sector 32-byte stores
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint32_t v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __float_as_uint(__uint_as_float(acc[j + u]) * alpha);
+          st_global_v8(o + j, v);
+        }
+      } else if (vec) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 v = make_float4(__uint_as_float(acc[j]) * alpha, __uint_as_float(acc[j + 1]) * alpha,
@@ -155,7 +164,16 @@ struct GemmPolicy {
       }
     } else if constexpr (EPI == EPI_BF16_STORE) {
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(r) * p.ldo + cb;
-      if ((cb + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      if ((cb + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 31) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 16) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            pk[u] = pack_bf16x2(__uint_as_float(acc[j + 2 * u]) * alpha, __uint_as_float(acc[j + 2 * u + 1]) * alpha);
+          st_global_v8(o + j, pk);
+        }
+      } else if ((cb + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           const uint4 pk = make_uint4(
@@ -327,7 +345,8 @@ struct ConvPolicy {
 
   // One 32-column chunk of one pixel: 64 contiguous bytes, written as two 32-byte stores.
   __device__ static void epilogue(const Params& p, const Ctx& c, const RowCtx& rc, int row, int col0,
-                                  const uint32_t (&acc)[32], float* sm, const uint32_t* premask = nullptr) {
+                                  const uint32_t (&acc)[32], float* sm, const uint32_t* premask = nullptr,
+                                  float* keep = nullptr, bool keep_on = false) {
     const int ch = c.c0 + col0;
     const bool valid = rc.valid && ch < p.Cn;
     const long long off = rc.pix_off + ch;
@@ -385,23 +404,32 @@ struct ConvPolicy {
       }
     }
     if (colsum) {
-      // Transpose-reduce across the warp with shuffles (recursive halving, 31 SHFL): afterwards
-      // lane l holds the sum over the warp's 32 pixels of column l.  No shared-memory traffic --
-      // the operand staging already saturates it.
-      __syncwarp();
+      if (keep_on) {         // caller keeps per-thread running sums and flushes once (colsum_flush)
 #pragma unroll
-      for (int s = 16; s >= 1; s >>= 1) {
-        const bool upper = (lane & s) != 0;
-#pragma unroll
-        for (int i = 0; i < s; ++i) {
-          const float keep = upper ? cs[i + s] : cs[i];
-          const float send = upper ? cs[i] : cs[i + s];
-          cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
+        for (int i = 0; i < 32; ++i) keep[i] += cs[i];
+      } else {
+        colsum_flush(p, c.c0 + col0, lane, cs, sm);
       }
-      const int cc = c.c0 + col0 + lane;
-      if (cc < p.Cn && cc < EPI_MAXC) atomicAdd(sm + cc, cs[0]);
     }
+  }
+
+  // Transpose-reduce across the warp with shuffles (recursive halving, 31 SHFL): afterwards lane l
+  // holds the sum over the warp's 32 pixels of column l, added to the per-CTA sums in shared
+  // memory.  No shared-memory traffic for the reduction itself -- operand staging saturates it.
+  __device__ static void colsum_flush(const Params& p, int ch0, int lane, float (&cs)[32], float* sm) {
+    __syncwarp();
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const bool upper = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+        const float keep = upper ? cs[i + s] : cs[i];
+        const float send = upper ? cs[i] : cs[i + s];
+        cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+    const int cc = ch0 + lane;
+    if (cc < p.Cn && cc < EPI_MAXC) atomicAdd(sm + cc, cs[0]);
   }
 };
 
