@@ -74,6 +74,23 @@ def test_gemm_mnmn_store(M, N, K):
     assert rel_err(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("M,N,K,off", [(128, 64, 64, 0), (4096, 1024, 64, 0), (512, 256, 96, 8), (256, 72, 64, 0),
+                                       (24, 512, 64, 4)])
+def test_gemm_mnmn_bf16_store(M, N, K, off):
+    """FC wgrad written straight to the bf16 wire: out = bf16(alpha * dY^T X).  ``off`` shifts the
+    output start by a few elements (32-byte vs 16-byte vs scalar store paths), N=72 is ragged."""
+    ops = _ops()
+    torch.manual_seed(4)
+    A_km = bf(torch.randn(K, M, device=DEV))
+    B_kn = bf(torch.randn(K, N, device=DEV))
+    buf = torch.full((M * N + 64,), 7.0, dtype=torch.bfloat16, device=DEV)
+    out = buf[off:off + M * N].view(M, N)
+    ops.gemm(A_km, B_kn, out, M=M, N=N, K=K, a_mn=True, b_mn=True, epi="bf16_store", alpha=0.125)
+    ref = 0.125 * (A_km.float().t() @ B_kn.float())
+    assert rel_err(out, ref) < 1e-2
+    assert bool((buf[:off] == 7.0).all()) and bool((buf[off + M * N:] == 7.0).all())
+
+
 def test_gemm_bf16_bias_relu():
     """Layer-0 im2col GEMM: bf16(relu(A W^T + b))."""
     ops = _ops()
