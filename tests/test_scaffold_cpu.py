@@ -319,3 +319,34 @@ def test_emulated_reference_tracks_autograd():
         a, b = grads[name].flatten(), p.grad.flatten()
         cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
         assert cos > 0.9, (name, cos)       # bf16 rounding drift grows towards the input layers
+
+
+def test_coil100_regrouping(tmp_path):
+    """tools/coil100: the reference's hand-made 3-class split of COIL-100 (Readme.md:81-107)."""
+    from PIL import Image
+
+    from distributed_vgg_f_b200.data.folder import scan_image_folder
+    from distributed_vgg_f_b200.tools import coil100
+
+    src = tmp_path / "coil-100"
+    src.mkdir()
+    for obj in (2, 6, 1, 100, 47, 99):                  # edible, toy, other, toy, edible, other
+        for angle in range(0, 50, 5):                   # 10 views each
+            Image.new("RGB", (8, 8), (obj, angle, 0)).save(src / ("obj%d__%d.png" % (obj, angle)))
+    (src / "readme.txt").write_text("not an image")
+    assert len(coil100.EDIBLE) == 18 and len(coil100.TOY) == 20           # 1296 / 1440 images of 72 views
+    assert (len(coil100.EDIBLE) * 72, len(coil100.TOY) * 72, (100 - 38) * 72) == (1296, 1440, 4464)
+    rep = coil100.prepare(str(src), str(tmp_path / "coil3"), val_fraction=0.2, seed=0)
+    assert rep == {c: {"train": 16, "val": 4} for c in ("edible", "other", "toy")}
+    classes, samples = scan_image_folder(str(tmp_path / "coil3" / "TrainData"))
+    assert classes == ["edible", "other", "toy"] and len(samples) == 48
+    _, val = scan_image_folder(str(tmp_path / "coil3" / "ValidationData"))
+    train_names = {os.path.basename(p) for p, _ in samples}
+    assert not train_names & {os.path.basename(p) for p, _ in val}      # disjoint split
+    assert all(os.path.basename(p).startswith(("obj2__", "obj47__")) for p, y in samples if y == 0)
+    # idempotent, and the weights follow 1/count
+    assert coil100.prepare(str(src), str(tmp_path / "coil3"), val_fraction=0.2, seed=0) == rep
+    w = coil100.inverse_frequency_weights({"edible": 1037, "other": 3571, "toy": 1152})
+    assert abs(sum(w) - 1.0) < 1e-3 and w[1] < w[2] < w[0]
+    assert coil100.main([str(src), str(tmp_path / "c2"), "--copy"]) == 0
+    assert not os.path.islink(str(tmp_path / "c2" / "TrainData" / "toy" / os.listdir(str(tmp_path / "c2" / "TrainData" / "toy"))[0]))
