@@ -11,7 +11,9 @@ Same surface here, two pipelines:
   * ``pipeline="fused"`` (default) -- every image is decoded ONCE into a uint8 cache (thread pool),
     a background thread gathers each batch into a pinned staging ring together with the sampled
     transform parameters, and the consumer runs the fused augment op on the device.  Yields
-    ``FusedBatch``.  Requires a uniform source size (true for COIL-100 / the synthetic set).
+    ``FusedBatch``.  Requires a uniform source size (true for COIL-100 / the synthetic set) and a
+    split that fits in host memory; ``pipeline="auto"`` (the CLI default) switches to the
+    reference pipeline when either does not hold.
 Ragged final batches are preserved (``drop_last=False`` in the reference).
 """
 from __future__ import annotations
@@ -51,11 +53,36 @@ def _decode(path: str) -> np.ndarray:
         return np.asarray(Image.open(f).convert("RGB"), dtype=np.uint8)
 
 
+class CacheUnavailable(ValueError):
+    """The split cannot be held as one uint8 tensor (mixed image sizes, or too big for host RAM)."""
+
+
+def _cache_budget_bytes() -> int:
+    """B200_MAX_CACHE_GB, else half of the memory the OS reports as available (at most 64 GB)."""
+    env = os.environ.get("B200_MAX_CACHE_GB")
+    if env:
+        return int(float(env) * (1 << 30))
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return min(int(line.split()[1]) * 1024 // 2, 64 << 30)
+    except OSError:
+        pass
+    return 16 << 30
+
+
 class DecodedCache:
     """All images of a split, decoded once to uint8 HWC (optionally by the native PNG decoder)."""
 
-    def __init__(self, samples: List[Tuple[str, int]], threads: int = 8) -> None:
+    def __init__(self, samples: List[Tuple[str, int]], threads: int = 8, max_bytes: Optional[int] = None) -> None:
         paths = [p for p, _ in samples]
+        if paths:          # size the cache from the first image before decoding everything
+            h, w, _ = _decode(paths[0]).shape
+            need, budget = len(paths) * h * w * 3, (_cache_budget_bytes() if max_bytes is None else max_bytes)
+            if need > budget:
+                raise CacheUnavailable("decoded cache needs %.1f GB for %d images of %dx%d, budget %.1f GB "
+                                       "(B200_MAX_CACHE_GB)" % (need / 2**30, len(paths), h, w, budget / 2**30))
         images = None
         try:   # native multi-threaded PNG decode (csrc/png_decode.cpp), falls back to PIL
             from ..ops import native_decode_pngs
@@ -68,8 +95,8 @@ class DecodedCache:
                 arrays = list(ex.map(_decode, paths))
             shapes = {a.shape for a in arrays}
             if len(shapes) != 1:
-                raise ValueError("fused pipeline needs a uniform image size, found %s; "
-                                 "use pipeline='reference'" % sorted(shapes)[:4])
+                raise CacheUnavailable("fused pipeline needs a uniform image size, found %s; "
+                                       "use pipeline='reference'" % sorted(shapes)[:4])
             images = torch.from_numpy(np.stack(arrays))
         self.images = images                                          # [N,H,W,3] uint8
         self.labels = torch.tensor([l for _, l in samples], dtype=torch.int64)
@@ -260,13 +287,24 @@ class DataManager:
                                      reference_order=reference_order)
         elif shard_eval and world_size > 1:   # extension: exact partition, metrics all-reduced
             sampler = ShardedSampler(self.data_size, world_size, rank, shuffle=False, pad=False)
+        if pipeline in ("fused", "auto"):
+            try:
+                self.cache = DecodedCache(self.samples, decode_threads)
+            except CacheUnavailable as e:
+                if pipeline == "fused":
+                    raise
+                # mixed sizes / larger than host memory: the reference's per-sample PIL pipeline
+                # handles anything an ImageFolder can hold (every rank sees the same files, so
+                # every rank takes the same branch)
+                print("[Info] %s -> using the per-sample (reference) input pipeline" % e, flush=True)
+                pipeline = "reference"
+        self.pipeline = pipeline = "fused" if pipeline == "auto" else pipeline
         if pipeline == "fused":
-            self.cache = DecodedCache(self.samples, decode_threads)
             self.loader = _FusedLoader(self.cache, mini_batch, train, sampler, True, seed)
         elif pipeline == "reference":
             self.loader = _ReferenceLoader(self.samples, mini_batch, train, sampler, True, seed)
         else:
-            raise ValueError("pipeline must be 'fused' or 'reference'")
+            raise ValueError("pipeline must be 'fused', 'reference' or 'auto'")
 
     def get_loader(self):
         return self.loader

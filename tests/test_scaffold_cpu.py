@@ -350,3 +350,31 @@ def test_coil100_regrouping(tmp_path):
     assert abs(sum(w) - 1.0) < 1e-3 and w[1] < w[2] < w[0]
     assert coil100.main([str(src), str(tmp_path / "c2"), "--copy"]) == 0
     assert not os.path.islink(str(tmp_path / "c2" / "TrainData" / "toy" / os.listdir(str(tmp_path / "c2" / "TrainData" / "toy"))[0]))
+
+
+def test_auto_pipeline_falls_back_for_mixed_sizes_and_big_splits(synth_root, tmp_path, monkeypatch, capsys):
+    """pipeline='auto': mixed image sizes or a split larger than the cache budget use the per-sample
+    pipeline (which is what the reference always does); pipeline='fused' reports the reason."""
+    import shutil
+
+    from PIL import Image
+
+    from distributed_vgg_f_b200.data.loader import CacheUnavailable, DataManager, FusedBatch
+
+    dm = DataManager(synth_root, 4, train=True, pipeline="auto")
+    assert dm.pipeline == "fused" and isinstance(next(iter(dm.get_loader())), FusedBatch)
+    monkeypatch.setenv("B200_MAX_CACHE_GB", "0.00001")
+    dm = DataManager(synth_root, 4, train=True, pipeline="auto")
+    assert dm.pipeline == "reference" and "B200_MAX_CACHE_GB" in capsys.readouterr().out
+    x, y = next(iter(dm.get_loader()))
+    assert tuple(x.shape) == (4, 3, 224, 224) and x.dtype == torch.float32 and y.dtype == torch.int64
+    with pytest.raises(CacheUnavailable):
+        DataManager(synth_root, 4, train=True, pipeline="fused")
+    monkeypatch.delenv("B200_MAX_CACHE_GB")
+    mixed = str(tmp_path / "mixed")
+    shutil.copytree(synth_root, mixed)
+    cls_dir = os.path.join(mixed, "TrainData", "toy")
+    Image.new("RGB", (96, 160), (10, 200, 30)).save(os.path.join(cls_dir, "odd_size.png"))
+    dm = DataManager(mixed, 4, train=True, pipeline="auto")
+    assert dm.pipeline == "reference" and dm.data_size == len(dm.samples)
+    assert sum(int(yb.numel()) for _, yb in dm.get_loader()) == dm.data_size
