@@ -65,7 +65,7 @@ __global__ void cross_entropy_kernel(const float* __restrict__ logits, const lon
       }
     }
     if (lane == 0) {
-      loss_acc += lse - row[t];
+      loss_acc += w * (lse - row[t]);
       correct_acc += (amax == t) ? 1.f : 0.f;
     }
   }
@@ -74,12 +74,15 @@ __global__ void cross_entropy_kernel(const float* __restrict__ logits, const lon
   if (threadIdx.x == 0) {
     float tl = 0.f, tc = 0.f;
     for (int i = 0; i < nwarps; ++i) { tl += s_loss[i]; tc += s_correct[i]; }
+    // batch loss as torch reports it: mean over the batch, or sum_i w_i nll_i / sum_i w_i with
+    // class weights; the meter accumulates loss * B like Average.update(loss.item(), B)
+    const float mean = cw ? tl / s_total_w : tl / static_cast<float>(B);
     if (meter) {
-      atomicAdd(meter + 0, tl);
+      atomicAdd(meter + 0, mean * static_cast<float>(B));
       atomicAdd(meter + 1, tc);
       atomicAdd(meter + 2, static_cast<float>(B));
     }
-    if (loss_out) *loss_out = tl / static_cast<float>(B);
+    if (loss_out) *loss_out = mean;
   }
 }
 

@@ -102,7 +102,7 @@ class Trainer:
             if wrapper is not None:
                 wrapper.finish_backward()
             self.optimizer.step()
-            meter.add_reference(outputs.detach(), targets)
+            meter.add_reference(outputs.detach(), targets, self.class_weights)
         return meter.snapshot()
 
     def _reduce_eval(self, meter: DeviceMeter):

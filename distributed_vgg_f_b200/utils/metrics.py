@@ -68,11 +68,18 @@ class DeviceMeter:
     def reset(self) -> None:
         self.buf.zero_()
 
-    def add_reference(self, logits: torch.Tensor, target: torch.Tensor) -> None:
-        """Torch-op fallback used by the oracle path (same arithmetic as the kernel)."""
+    def add_reference(self, logits: torch.Tensor, target: torch.Tensor, weight=None) -> None:
+        """Torch-op fallback used by the oracle path (same arithmetic as the kernel): accumulates
+        ``loss * batch`` exactly like ``Average.update(loss.item(), batch)`` in the reference's loop,
+        where ``loss`` is the (optionally class-weighted) mean torch reports."""
         with torch.no_grad():
             logp = torch.log_softmax(logits.float(), dim=1)
-            self.buf[0] += -logp.gather(1, target.view(-1, 1)).sum()
+            nll = -logp.gather(1, target.view(-1, 1)).view(-1)
+            if weight is None:
+                self.buf[0] += nll.sum()
+            else:
+                w = weight.to(nll.device, nll.dtype)[target]
+                self.buf[0] += (w * nll).sum() / w.sum() * logits.shape[0]
             self.buf[1] += logits.argmax(dim=1).eq(target).sum()
             self.buf[2] += logits.shape[0]
 

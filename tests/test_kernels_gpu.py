@@ -298,6 +298,28 @@ def test_cross_entropy(B, C):
     assert int(meter[2]) == B
 
 
+@pytest.mark.parametrize("B,C", [(64, 3), (33, 10)])
+def test_cross_entropy_class_weights(B, C):
+    """The reference's optional weighted loss (distributedVggf.py:164-166): torch semantics,
+    loss = sum_i w[y_i] nll_i / sum_i w[y_i], and the gradient that goes with it."""
+    ops = _ops()
+    torch.manual_seed(1)
+    logits = torch.randn(B, C, device=DEV) * 2
+    target = torch.randint(0, C, (B,), device=DEV)
+    w = torch.rand(C, device=DEV) + 0.1
+    ldd = (C + 7) // 8 * 8
+    dl = torch.empty(B, ldd, dtype=torch.bfloat16, device=DEV)
+    meter = torch.zeros(4, device=DEV)
+    loss = torch.zeros(1, device=DEV)
+    ops.cross_entropy(logits, target, dl, ldd, meter, loss, class_weights=w)
+    lr = logits.clone().requires_grad_(True)
+    ref = F.cross_entropy(lr, target, weight=w)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-4
+    assert rel_err(dl[:, :C], lr.grad) < 1e-2
+    assert abs(float(meter[0]) - float(ref) * B) < 1e-2 and int(meter[2]) == B
+
+
 def test_adam_matches_torch():
     ops = _ops()
     torch.manual_seed(0)

@@ -378,3 +378,22 @@ def test_auto_pipeline_falls_back_for_mixed_sizes_and_big_splits(synth_root, tmp
     dm = DataManager(mixed, 4, train=True, pipeline="auto")
     assert dm.pipeline == "reference" and dm.data_size == len(dm.samples)
     assert sum(int(yb.numel()) for _, yb in dm.get_loader()) == dm.data_size
+
+
+def test_weighted_loss_readout_matches_torch():
+    """With --class-weights the epoch loss is the weighted mean torch reports (what the reference's
+    commented-out variant would feed to Average.update), evaluation stays unweighted."""
+    import torch.nn.functional as F
+
+    from distributed_vgg_f_b200.utils.metrics import DeviceMeter
+
+    g = torch.Generator().manual_seed(0)
+    w = torch.tensor([0.41, 0.19, 0.4])                   # distributedUtil.py:28
+    m, expect, n = DeviceMeter("cpu"), 0.0, 0
+    for b in (5, 3):
+        logits, y = torch.randn(b, 3, generator=g), torch.randint(0, 3, (b,), generator=g)
+        m.add_reference(logits, y, w)
+        expect += float(F.cross_entropy(logits, y, weight=w)) * b
+        n += b
+    avg, acc = m.snapshot()
+    assert abs(avg.sum - expect) < 1e-5 and avg.count == n and acc.count == n
