@@ -41,6 +41,35 @@ static void conv_fprop(const at::Tensor& x, const at::Tensor& w, c10::optional<a
   TORCH_CHECK(w.numel() == (int64_t)Cout * 9 * Cin && y.numel() == (int64_t)N * H * W * Cout, "conv_fprop: shape mismatch");
   b200::conv3x3_fprop(bfp(x), bfp(w), f32p_opt(bias), bfp_mut(y), N, H, W, Cin, Cout, relu, (int)bn, cur_stream());
 }
+// EXPERIMENTAL (B200_FUSE_POOL=1): pooled activation + int32 mask words [N,H/2,W/2,Cout/32,4]
+static void conv_fprop_pool(const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias,
+                            at::Tensor pooled, at::Tensor mask, int64_t bn) {
+  c10::cuda::CUDAGuard g(x.device());
+  TORCH_CHECK(x.dim() == 4 && x.is_contiguous() && w.is_contiguous() && pooled.is_contiguous() && mask.is_contiguous(),
+              "conv_fprop_pool: contiguous NHWC");
+  const int N = x.size(0), H = x.size(1), W = x.size(2), Cin = x.size(3), Cout = w.size(0);
+  TORCH_CHECK(w.numel() == (int64_t)Cout * 9 * Cin && pooled.numel() == (int64_t)N * (H / 2) * (W / 2) * Cout &&
+                  pooled.scalar_type() == at::kBFloat16,
+              "conv_fprop_pool: shape mismatch");
+  TORCH_CHECK(mask.scalar_type() == at::kInt && mask.numel() == (int64_t)N * (H / 2) * (W / 2) * (Cout / 32) * 4,
+              "conv_fprop_pool: mask must be int32 [N,H/2,W/2,Cout/32,4]");
+  b200::conv3x3_fprop_pool(bfp(x), bfp(w), f32p_opt(bias), bfp_mut(pooled),
+                           reinterpret_cast<uint32_t*>(mask.data_ptr<int>()), N, H, W, Cin, Cout, (int)bn, cur_stream());
+}
+static bool conv_pool_fusable(int64_t N, int64_t H, int64_t W) { return b200::conv3x3_pool_fusable((int)N, (int)H, (int)W); }
+static void unpool(const at::Tensor& dp, const at::Tensor& mask, at::Tensor dz, c10::optional<at::Tensor> colsum) {
+  c10::cuda::CUDAGuard g(dp.device());
+  TORCH_CHECK(dp.dim() == 4 && dz.dim() == 4 && dp.is_contiguous() && dz.is_contiguous() && mask.is_contiguous() &&
+                  mask.scalar_type() == at::kInt,
+              "unpool2x2: contiguous NHWC bf16 + int32 mask");
+  const int N = dz.size(0), H = dz.size(1), W = dz.size(2), C = dz.size(3);
+  TORCH_CHECK(dp.size(0) == N && dp.size(1) == H / 2 && dp.size(2) == W / 2 && dp.size(3) == C &&
+                  mask.numel() == (int64_t)N * (H / 2) * (W / 2) * (C / 32) * 4,
+              "unpool2x2: shape mismatch");
+  b200::unpool2x2(bfp(dp), reinterpret_cast<const uint32_t*>(mask.data_ptr<int>()), bfp_mut(dz), f32p_opt(colsum), N, H,
+                  W, C, cur_stream());
+}
+
 static void conv_dgrad(const at::Tensor& dz, const at::Tensor& w, c10::optional<at::Tensor> mask, at::Tensor dx,
                        c10::optional<at::Tensor> colsum, int64_t bn) {
   c10::cuda::CUDAGuard g(dz.device());
@@ -300,6 +329,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv0_fprop", &conv0_fprop);
   m.def("conv0_wgrad", &conv0_wgrad);
   m.def("conv_fprop", &conv_fprop);
+  m.def("conv_fprop_pool", &conv_fprop_pool);
+  m.def("conv_pool_fusable", &conv_pool_fusable);
+  m.def("unpool2x2", &unpool);
   m.def("conv_dgrad", &conv_dgrad);
   m.def("conv_wgrad", &conv_wgrad);
   m.def("maxpool_fwd", &maxpool_fwd);

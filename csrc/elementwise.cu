@@ -143,6 +143,70 @@ void maxpool2x2_relu_bwd(const bf16* y, const bf16* dp, bf16* dz, float* colsum,
   check_last("maxpool2x2_relu_bwd");
 }
 
+// EXPERIMENTAL: backward of the pool fused into the conv epilogue (ConvPolicy::epilogue_pool).  One
+// thread = one pooled pixel x 8 channels: reads 16 B of dp and the chunk's mask words, writes the
+// four 16-byte pieces of dz.  Reads 3/8 of a full-resolution tensor instead of 1 1/2.
+__global__ void unpool2x2_kernel(const bf16* __restrict__ dp, const uint32_t* __restrict__ mask,
+                                 bf16* __restrict__ dz, float* __restrict__ colsum, int N, int H, int W,
+                                 int C) {
+  extern __shared__ float s_sum[];      // [C] when colsum
+  const int OH = H / 2, OW = W / 2, C8 = C / 8, C32 = C / 32;
+  const long long total = static_cast<long long>(N) * OH * OW * C8;
+  float bsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (colsum) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_sum[i] = 0.f;
+    __syncthreads();
+  }
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = i % C8;
+    long long r = i / C8;                                   // pooled pixel index
+    const long long ppix = r;
+    const int ow = r % OW; r /= OW;
+    const int oh = r % OH;
+    const int n = r / OH;
+    const uint4 mk = *reinterpret_cast<const uint4*>(mask + (ppix * C32 + (c8 >> 2)) * 4);
+    const int sh = (c8 & 3) * 8;
+    const uint32_t b0 = mk.x >> sh, b1 = mk.y >> sh, pos = mk.z >> sh;
+    float g[8], ra[8], rb[8], rc[8], rd[8];
+    unpack8(ld_nc_v4(dp + ppix * C + c8 * 8), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float gg = ((pos >> k) & 1u) ? g[k] : 0.f;
+      const uint32_t idx = ((b0 >> k) & 1u) | (((b1 >> k) & 1u) << 1);
+      ra[k] = idx == 0u ? gg : 0.f; rb[k] = idx == 1u ? gg : 0.f;
+      rc[k] = idx == 2u ? gg : 0.f; rd[k] = idx == 3u ? gg : 0.f;
+      bsum[k] += gg;
+    }
+    const long long o00 = ((static_cast<long long>(n) * H + 2 * oh) * W + 2 * ow) * C + c8 * 8;
+    const long long rowstride = static_cast<long long>(W) * C;
+    *reinterpret_cast<uint4*>(dz + o00) = pack8(ra);
+    *reinterpret_cast<uint4*>(dz + o00 + C) = pack8(rb);
+    *reinterpret_cast<uint4*>(dz + o00 + rowstride) = pack8(rc);
+    *reinterpret_cast<uint4*>(dz + o00 + rowstride + C) = pack8(rd);
+  }
+  if (colsum) {
+    const int c8 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) % C8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_sum[c8 * 8 + k], bsum[k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x)
+      if (s_sum[i] != 0.f) atomicAdd(colsum + i, s_sum[i]);
+  }
+}
+
+void unpool2x2(const bf16* dp, const uint32_t* mask, bf16* dz, float* colsum, int N, int H, int W, int C,
+               cudaStream_t s) {
+  if (C % 32 || H % 2 || W % 2) throw std::runtime_error("[b200] unpool2x2: need C%32==0 and even H,W");
+  if (colsum && 256 % (C / 8) != 0)
+    throw std::runtime_error("[b200] unpool2x2: fused column sum needs C/8 to divide 256");
+  const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
+  const int blocks = min(ceil_div_ll(total, 256), 148 * 16);
+  unpool2x2_kernel<<<blocks, 256, colsum ? C * sizeof(float) : 0, s>>>(dp, mask, dz, colsum, N, H, W, C);
+  count_launch();
+  check_last("unpool2x2");
+}
+
 // ---------------------------------------------------------------------- adaptive average pool
 __device__ __forceinline__ int ap_start(int o, int in, int out) { return (o * in) / out; }
 __device__ __forceinline__ int ap_end(int o, int in, int out) { return ((o + 1) * in + out - 1) / out; }

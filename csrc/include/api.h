@@ -30,6 +30,13 @@ void conv0_wgrad(const bf16* dz, const bf16* x4, float* dw0, int N, int H, int W
 // 3x3 / stride 1 / pad 1 convolution, NHWC bf16, weights [Cout][3][3][Cin] bf16.
 void conv3x3_fprop(const bf16* x, const bf16* w, const float* bias, bf16* y, int N, int H, int W,
                    int Cin, int Cout, bool relu, int bn, cudaStream_t stream);
+// EXPERIMENTAL (B200_FUSE_POOL=1): conv + bias + ReLU + 2x2/2 max-pool in one kernel.  Writes the
+// pooled activation [N,H/2,W/2,Cout] and, per pooled pixel and 32 channels, four words {argmax bit 0,
+// argmax bit 1, max > 0, 0}; the un-pooled activation is never materialised.  unpool2x2 is the
+// matching backward (elementwise.cu).
+bool conv3x3_pool_fusable(int N, int H, int W);
+void conv3x3_fprop_pool(const bf16* x, const bf16* w, const float* bias, bf16* pool_out, uint32_t* pool_mask,
+                        int N, int H, int W, int Cin, int Cout, int bn, cudaStream_t stream);
 // dx[N,H,W,Cin] = conv_transpose(dz[N,H,W,Cout], w); optional mask: zero where mask_src <= 0;
 // optional colsum[Cin] += sum over pixels of dx (the previous layer's bias gradient, fused).
 void conv3x3_dgrad(const bf16* dz, const bf16* w, const bf16* mask_src, bf16* dx, float* colsum, int N,
@@ -48,6 +55,10 @@ void maxpool2x2_fwd(const bf16* x, bf16* y, int N, int H, int W, int C, cudaStre
 // optional colsum[C] += sum over pixels of dz (the layer's bias gradient, fused).
 void maxpool2x2_relu_bwd(const bf16* y, const bf16* dp, bf16* dz, float* colsum, int N, int H, int W,
                          int C, cudaStream_t s);
+// EXPERIMENTAL: backward of conv3x3_fprop_pool's pooling: dz[N,H,W,C] gets dp[N,H/2,W/2,C] at the
+// recorded argmax where the maximum was positive, zero elsewhere; optional colsum as above.
+void unpool2x2(const bf16* dp, const uint32_t* mask, bf16* dz, float* colsum, int N, int H, int W, int C,
+               cudaStream_t s);
 void adaptive_avgpool_fwd(const bf16* x, bf16* y, int N, int H, int W, int C, int OH, int OW,
                           cudaStream_t s);
 void adaptive_avgpool_bwd(const bf16* dy, bf16* dx, int N, int H, int W, int C, int OH, int OW,

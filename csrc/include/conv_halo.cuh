@@ -37,11 +37,11 @@ struct HaloCfg {
   static constexpr int SMEM = NA * HALO_SLOT + NB * B_SLOT + 1024 + BAR_BYTES;
 };
 
-template <int BN, bool DGRAD>
+template <int BN, bool DGRAD, bool POOL = false>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ ConvParams prm) {
   using Cfg = HaloCfg<BN>;
-  using Epi = ConvPolicy<BN, 1, DGRAD>;
+  using Epi = ConvPolicy<BN, 1, DGRAD, POOL>;
   constexpr int NA = Cfg::NA, NB = Cfg::NB, B_SLOT = Cfg::B_SLOT;
   constexpr uint32_t TMEM_COLS = umma_tmem_cols<BN>();
 

@@ -304,6 +304,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(t);

@@ -219,6 +219,8 @@ enum ConvFlags : int {
   CONV_MASK = 4,          // zero where mask_src <= 0 (ReLU backward fused into dgrad)
   CONV_COLSUM = 8,        // colsum[channel] += sum over pixels of the stored (bf16-rounded) output:
                           // the bias gradient of the previous layer, for free in the dgrad epilogue
+  CONV_POOL = 16,         // fprop only, EXPERIMENTAL (B200_FUSE_POOL=1): 2x2/2 max-pool inside the
+                          // epilogue -- writes pool_out + pool_mask, never the un-pooled tensor
 };
 
 struct ConvParams {
@@ -235,6 +237,8 @@ struct ConvParams {
   const float* bias;
   const __nv_bfloat16* mask_src;
   float* colsum;          // [Cn] fp32, accumulated with atomics (CONV_COLSUM)
+  __nv_bfloat16* pool_out;  // CONV_POOL: NHWC [N][H/2][W/2][Cn]
+  uint32_t* pool_mask;      // CONV_POOL: [N][H/2][W/2][Cn/32][4] = {argmax bit 0, argmax bit 1, max > 0, 0}
   int flags;
   int resident;           // halo kernel: all weight tiles stay in shared memory for the CTA lifetime
 };
@@ -249,8 +253,11 @@ __device__ __forceinline__ void conv_tile_origin(const ConvTile& t, int tile, in
   n0 = static_cast<int>(tn) * t.Nb;
 }
 
-template <int BN_, int STAGES_, bool DGRAD>
+// POOL (fprop only, experimental): a separate instantiation, so the default kernels stay exactly
+// the code that was profiled and validated.
+template <int BN_, int STAGES_, bool DGRAD, bool POOL = false>
 struct ConvPolicy {
+  static_assert(!(DGRAD && POOL), "the fused pool is an fprop epilogue");
   static constexpr int BN = BN_;
   static constexpr int STAGES = STAGES_;
   static constexpr bool A_MN = false;
@@ -347,6 +354,10 @@ struct ConvPolicy {
   __device__ static void epilogue(const Params& p, const Ctx& c, const RowCtx& rc, int row, int col0,
                                   const uint32_t (&acc)[32], float* sm, const uint32_t* premask = nullptr,
                                   float* keep = nullptr, bool keep_on = false) {
+    if constexpr (POOL) {
+      epilogue_pool(p, c, rc, row, col0, acc, sm);
+      return;
+    }
     const int ch = c.c0 + col0;
     const bool valid = rc.valid && ch < p.Cn;
     const long long off = rc.pix_off + ch;
@@ -410,6 +421,59 @@ struct ConvPolicy {
       } else {
         colsum_flush(p, c.c0 + col0, lane, cs, sm);
       }
+    }
+  }
+
+  // EXPERIMENTAL (CONV_POOL): bias + ReLU + 2x2/2 max-pool of one 32-channel chunk.  The TMEM lane
+  // is the pixel, a warp holds 32 consecutive tile rows = (32 / Wb) image rows of Wb pixels, so the
+  // four pixels of a pool window are lanes {l, l^1, l^Wb, l^Wb^1} (Wb <= 16, tile origin and image
+  // extent even: the launcher checks).  The top-left lane of each window stores the pooled bf16
+  // values and three bit masks per 32 channels: argmax position (2 bits, first maximum in the order
+  // (0,0) (0,1) (1,0) (1,1), like maxpool2x2_relu_bwd) and "max > 0" (the ReLU mask) -- everything
+  // the backward pass needs, so the un-pooled activation is never written.
+  __device__ static void epilogue_pool(const Params& p, const Ctx& c, const RowCtx& rc, int row, int col0,
+                                       const uint32_t (&acc)[32], float* sm) {
+    const ConvTile& t = p.t;
+    const int ch = c.c0 + col0;
+    const bool chan_ok = ch < p.Cn;                        // warp-uniform
+    uint32_t pk[16], m[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      float lo = __uint_as_float(acc[2 * u]), hi = __uint_as_float(acc[2 * u + 1]);
+      if (chan_ok && (p.flags & CONV_BIAS)) { lo += sm[ch + 2 * u]; hi += sm[ch + 2 * u + 1]; }
+      pk[u] = pack_bf16x2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) m[u] = max_bf16x2(pk[u], __shfl_xor_sync(0xffffffffu, pk[u], 1));
+#pragma unroll
+    for (int u = 0; u < 16; ++u) m[u] = max_bf16x2(m[u], __shfl_xor_sync(0xffffffffu, m[u], t.Wb));
+    uint32_t e = 0, pos = 0;                               // bit ch: my value is the window maximum / max > 0
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const uint32_t d = pk[u] ^ m[u];
+      e |= ((d & 0xffffu) == 0u ? 1u : 0u) << (2 * u);
+      e |= ((d >> 16) == 0u ? 1u : 0u) << (2 * u + 1);
+      pos |= ((m[u] & 0x7fffu) != 0u ? 1u : 0u) << (2 * u);
+      pos |= ((m[u] & 0x7fff0000u) != 0u ? 1u : 0u) << (2 * u + 1);
+    }
+    const uint32_t e1 = __shfl_xor_sync(0xffffffffu, e, 1);          // (0,1) as seen from the top-left lane
+    const uint32_t e2 = __shfl_xor_sync(0xffffffffu, e, t.Wb);       // (1,0)
+    const int ww = row & (t.Wb - 1);
+    const int r2 = row >> t.wb_shift;
+    const int hh = r2 & (t.Hb - 1);
+    const int nn = r2 >> t.hb_shift;
+    if (((ww | hh) & 1) == 0 && rc.valid && chan_ok) {
+      const int n = c.n0 + nn, h = c.h0 + hh, w = c.w0 + ww;
+      const long long ppix = (static_cast<long long>(n) * (t.H >> 1) + (h >> 1)) * (t.W >> 1) + (w >> 1);
+      __nv_bfloat16* o = p.pool_out + ppix * p.Cn + ch;
+      const uint32_t lo8[8] = {m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]};
+      const uint32_t hi8[8] = {m[8], m[9], m[10], m[11], m[12], m[13], m[14], m[15]};
+      st_global_v8(o, lo8);
+      st_global_v8(o + 16, hi8);
+      // first maximum: 0 if e, else 1 if e1, else 2 if e2, else 3
+      const uint32_t b0 = ~e & (e1 | ~e2);
+      const uint32_t b1 = ~e & ~e1;
+      *reinterpret_cast<uint4*>(p.pool_mask + (ppix * (p.Cn >> 5) + (ch >> 5)) * 4) = make_uint4(b0, b1, pos, 0u);
     }
   }
 

@@ -144,7 +144,7 @@ static bool halo_enabled() {
 // The halo kernel tiles the image in 8 x 16 pixel blocks: use it where that wastes nothing.
 static bool halo_applicable(int H, int W) { return halo_enabled() && W % HALO_WT == 0 && H % HALO_HT == 0 && W >= 32; }
 
-template <int BN, bool DGRAD>
+template <int BN, bool DGRAD, bool POOL = false>
 static void conv_halo_launch(ConvParams& prm, const bf16* act, cudaStream_t stream) {
   using Cfg = HaloCfg<BN>;
   ConvTile& t = prm.t;
@@ -157,16 +157,16 @@ static void conv_halo_launch(ConvParams& prm, const bf16* act, cudaStream_t stre
   prm.num_tiles = prm.tiles_m * tiles_n;
   prm.resident = (tiles_n == 1 && 9 * (prm.Ca / UMMA_BK) <= Cfg::NB) ? 1 : 0;
   map_nhwc_box(&prm.mapA, act, t.N, t.H, t.W, prm.Ca, HALO_PITCH, HALO_HT + 2, 1);
-  constexpr int smem = Cfg::SMEM + ConvPolicy<BN, 1, DGRAD>::EPI_SMEM;
+  constexpr int smem = Cfg::SMEM + ConvPolicy<BN, 1, DGRAD, POOL>::EPI_SMEM;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, DGRAD, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess)
       throw std::runtime_error(std::string("[b200] cudaFuncSetAttribute(halo): ") + cudaGetErrorString(e));
     configured = true;
   }
   dim3 grid(prm.num_tiles < num_sms() ? prm.num_tiles : num_sms());
-  conv_halo_kernel<BN, DGRAD><<<grid, UMMA_THREADS, smem, stream>>>(prm);
+  conv_halo_kernel<BN, DGRAD, POOL><<<grid, UMMA_THREADS, smem, stream>>>(prm);
   count_launch();
   check_last("conv_halo_kernel launch");
 }
@@ -272,10 +272,10 @@ static void check_channels(int c, const char* what) {
   if (c % 64 != 0) throw std::runtime_error(std::string("[b200] ") + what + " must be a multiple of 64");
 }
 
-template <int BN, bool DGRAD>
+template <int BN, bool DGRAD, bool POOL = false>
 static void conv_launch(ConvParams& prm, cudaStream_t stream) {
   constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
-  using P = ConvPolicy<BN, STAGES, DGRAD>;
+  using P = ConvPolicy<BN, STAGES, DGRAD, POOL>;
   const ConvTile& t = prm.t;
   const int tiles_n = (t.N + t.Nb - 1) / t.Nb;
   prm.tiles_m = t.tiles_w * t.tiles_h * tiles_n;
@@ -289,33 +289,57 @@ static int auto_bn(int cn, int bn) {
   return cn <= 64 ? 64 : (cn <= 128 ? 128 : 256);
 }
 
-void conv3x3_fprop(const bf16* x, const bf16* w, const float* bias, bf16* y, int N, int H, int W,
-                   int Cin, int Cout, bool relu, int bn, cudaStream_t stream) {
+static void fprop_impl(const bf16* x, const bf16* w, const float* bias, bf16* y, bf16* pool_out,
+                       uint32_t* pool_mask, int N, int H, int W, int Cin, int Cout, bool relu, int bn,
+                       cudaStream_t stream) {
   check_channels(Cin, "conv3x3_fprop Cin");
   check_channels(Cout, "conv3x3_fprop Cout");
   ConvParams prm;
   prm.t = make_tile(N, H, W, UMMA_BM);
   prm.Ca = Cin; prm.Cn = Cout; prm.wcols_per_tap = Cin;
   prm.out = y; prm.bias = bias; prm.mask_src = nullptr; prm.colsum = nullptr;
-  prm.flags = (bias ? CONV_BIAS : 0) | (relu ? CONV_RELU : 0);
+  prm.pool_out = pool_out; prm.pool_mask = pool_mask;
+  prm.flags = (bias ? CONV_BIAS : 0) | (relu ? CONV_RELU : 0) | (pool_out ? CONV_POOL : 0);
   bn = auto_bn(Cout, bn);
   prm.resident = 0;
   map_2d(&prm.mapB, w, Cout, 9LL * Cin, 9LL * Cin, 64, bn);
+  const bool pool = pool_out != nullptr;
   if (halo_applicable(H, W)) {
     switch (bn) {
-      case 64: conv_halo_launch<64, false>(prm, x, stream); return;
-      case 128: conv_halo_launch<128, false>(prm, x, stream); return;
-      case 256: conv_halo_launch<256, false>(prm, x, stream); return;
+      case 64: pool ? conv_halo_launch<64, false, true>(prm, x, stream) : conv_halo_launch<64, false>(prm, x, stream); return;
+      case 128: pool ? conv_halo_launch<128, false, true>(prm, x, stream) : conv_halo_launch<128, false>(prm, x, stream); return;
+      case 256: pool ? conv_halo_launch<256, false, true>(prm, x, stream) : conv_halo_launch<256, false>(prm, x, stream); return;
       default: throw std::runtime_error("[b200] conv3x3_fprop: bn must be 64/128/256");
     }
   }
   map_nhwc(&prm.mapA, x, N, H, W, Cin, prm.t.Wb, prm.t.Hb, prm.t.Nb);
   switch (bn) {
-    case 64: conv_launch<64, false>(prm, stream); break;
-    case 128: conv_launch<128, false>(prm, stream); break;
-    case 256: conv_launch<256, false>(prm, stream); break;
+    case 64: pool ? conv_launch<64, false, true>(prm, stream) : conv_launch<64, false>(prm, stream); break;
+    case 128: pool ? conv_launch<128, false, true>(prm, stream) : conv_launch<128, false>(prm, stream); break;
+    case 256: pool ? conv_launch<256, false, true>(prm, stream) : conv_launch<256, false>(prm, stream); break;
     default: throw std::runtime_error("[b200] conv3x3_fprop: bn must be 64/128/256");
   }
+}
+
+void conv3x3_fprop(const bf16* x, const bf16* w, const float* bias, bf16* y, int N, int H, int W,
+                   int Cin, int Cout, bool relu, int bn, cudaStream_t stream) {
+  fprop_impl(x, w, bias, y, nullptr, nullptr, N, H, W, Cin, Cout, relu, bn, stream);
+}
+
+// EXPERIMENTAL: the pool windows must lie inside one epilogue warp (see ConvPolicy::epilogue_pool).
+bool conv3x3_pool_fusable(int N, int H, int W) {
+  if (H % 2 || W % 2) return false;
+  if (halo_applicable(H, W)) return true;               // 8 x 16 tiles
+  const ConvTile t = make_tile(N, H, W, UMMA_BM);
+  return t.Wb <= 16 && t.Hb >= 2 && W % t.Wb == 0 && H % t.Hb == 0;
+}
+
+void conv3x3_fprop_pool(const bf16* x, const bf16* w, const float* bias, bf16* pool_out, uint32_t* pool_mask,
+                        int N, int H, int W, int Cin, int Cout, int bn, cudaStream_t stream) {
+  if (!conv3x3_pool_fusable(N, H, W))
+    throw std::runtime_error("[b200] conv3x3_fprop_pool: this image size cannot fuse the 2x2 pool");
+  if (!pool_out || !pool_mask) throw std::runtime_error("[b200] conv3x3_fprop_pool: missing outputs");
+  fprop_impl(x, w, bias, nullptr, pool_out, pool_mask, N, H, W, Cin, Cout, true, bn, stream);
 }
 
 void conv3x3_dgrad(const bf16* dz, const bf16* w, const bf16* mask_src, bf16* dx, float* colsum, int N,
@@ -326,6 +350,7 @@ void conv3x3_dgrad(const bf16* dz, const bf16* w, const bf16* mask_src, bf16* dx
   prm.t = make_tile(N, H, W, UMMA_BM);
   prm.Ca = Cout; prm.Cn = Cin; prm.wcols_per_tap = Cin;
   prm.out = dx; prm.bias = nullptr; prm.mask_src = mask_src; prm.colsum = colsum;
+  prm.pool_out = nullptr; prm.pool_mask = nullptr;
   prm.flags = (mask_src ? CONV_MASK : 0) | (colsum ? CONV_COLSUM : 0);
   if (colsum && Cin > 512) throw std::runtime_error("[b200] conv3x3_dgrad: fused column sum supports Cin <= 512");
   bn = auto_bn(Cin, bn);

@@ -241,9 +241,17 @@ class NativeEngine:
         self.x_nhwc = torch.empty(B, HW, HW, 4, dtype=BF16, device=dev)
         self.acts: List[torch.Tensor] = []      # post-ReLU conv outputs
         self.pools: List[Optional[torch.Tensor]] = []
+        # EXPERIMENTAL, off unless B200_FUSE_POOL=1: the pooled layers' conv epilogue pools in
+        # registers and records argmax / ReLU bit masks; the un-pooled activation is never written
+        # (acts[i] of such a layer then holds stale data) and backward is an "unpool" kernel.
+        want_fused_pool = os.environ.get("B200_FUSE_POOL", "0") == "1"
+        self.pool_masks: List[Optional[torch.Tensor]] = []
         h = HW
-        for c in spec.convs:
+        for i, c in enumerate(spec.convs):
             self.acts.append(torch.empty(B, h, h, c.cout, dtype=BF16, device=dev))
+            fused = (want_fused_pool and c.pool_after and i > 0 and c.cout % 32 == 0
+                     and bool(ops.require().conv_pool_fusable(B, h, h)))
+            self.pool_masks.append(ops.pool_mask_like(B, h, h, c.cout, dev) if fused else None)
             if c.pool_after:
                 h //= 2
                 self.pools.append(torch.empty(B, h, h, c.cout, dtype=BF16, device=dev))
@@ -343,6 +351,10 @@ class NativeEngine:
         if c0.pool_after:
             x = ops.maxpool2x2(x, out=self.pools[0][:b])
         for i, c in enumerate(spec.convs[1:], start=1):
+            if self.pool_masks[i] is not None:           # experimental fused conv + ReLU + pool
+                x, _ = ops.conv3x3_fprop_pool(x, self._w(c.name), self._b(c.name), out=self.pools[i][:b],
+                                              mask=self.pool_masks[i][:b])
+                continue
             y = self.acts[i][:b]
             C.conv_fprop(x, self._w(c.name), self._b(c.name), y, True, 0)
             x = y
@@ -425,7 +437,10 @@ class NativeEngine:
             if c.pool_after:
                 dz = self.dbuf[pp][:y.numel()].view_as(y)
                 # ReLU + pool backward, bias gradient (column sum of dz) fused
-                ops.maxpool2x2_relu_bwd(y, g, out=dz, colsum=self._grad(c.name + ".bias"))
+                if self.pool_masks[i] is not None:
+                    ops.unpool2x2(g, self.pool_masks[i][:b], out=dz, colsum=self._grad(c.name + ".bias"))
+                else:
+                    ops.maxpool2x2_relu_bwd(y, g, out=dz, colsum=self._grad(c.name + ".bias"))
                 pp ^= 1
                 bias_fused = True
             else:

@@ -64,6 +64,30 @@ def conv3x3_fprop(x, w, bias, relu: bool = True, bn: int = 0, out=None):
     return y
 
 
+def pool_mask_like(n: int, h: int, w: int, c: int, device) -> torch.Tensor:
+    """Mask buffer of conv3x3_fprop_pool for an un-pooled [n,h,w,c] activation."""
+    return torch.zeros(n, h // 2, w // 2, c // 32, 4, dtype=torch.int32, device=device)
+
+
+def conv3x3_fprop_pool(x, w, bias, bn: int = 0, out=None, mask=None):
+    """EXPERIMENTAL (B200_FUSE_POOL=1): maxpool2x2(relu(conv(x) + bias)) without materialising the
+    un-pooled tensor.  Returns (pooled bf16 [N,H/2,W/2,Cout], mask int32 [N,H/2,W/2,Cout/32,4])."""
+    N, H, W, _ = x.shape
+    cout = w.shape[0]
+    p = out if out is not None else torch.empty(N, H // 2, W // 2, cout, dtype=torch.bfloat16, device=x.device)
+    m = mask if mask is not None else pool_mask_like(N, H, W, cout, x.device)
+    require().conv_fprop_pool(x, w, bias, p, m, bn)
+    return p, m
+
+
+def unpool2x2(dp, mask, out=None, colsum=None):
+    """Backward of the fused pool: route dp to the recorded argmax where the maximum was > 0."""
+    N, OH, OW, Cc = dp.shape
+    dz = out if out is not None else torch.empty(N, OH * 2, OW * 2, Cc, dtype=dp.dtype, device=dp.device)
+    require().unpool2x2(dp, mask, dz, colsum)
+    return dz
+
+
 def conv3x3_dgrad(dz, w, cin: int, mask_src=None, bn: int = 0, out=None, colsum=None):
     """dx = conv_transpose(dz, w) [* (mask_src > 0)]; colsum (fp32 [cin]) += dx.sum(pixels)."""
     N, H, W, _ = dz.shape

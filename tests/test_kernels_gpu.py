@@ -4,6 +4,7 @@ bf16 operands: inputs are rounded to bf16 first, the reference is evaluated in f
 rounded values, so the only differences are accumulation order and the final bf16 rounding.
 """
 import math
+import os
 
 import pytest
 import torch
@@ -198,6 +199,31 @@ def test_conv0_fused(N, H, W):
 
 
 # ------------------------------------------------------------------------------------- pointwise
+EXPERIMENTAL = pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL", "0") != "1",
+                                  reason="experimental kernels: set B200_EXPERIMENTAL=1")
+
+
+@EXPERIMENTAL
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 32, 32, 64, 64), (1, 48, 64, 128, 128), (2, 56, 56, 64, 128),
+                                            (3, 28, 28, 128, 256), (4, 14, 14, 512, 512), (1, 224, 224, 64, 64)])
+def test_conv_fprop_pool_fused(N, H, W, Cin, Cout):
+    """conv + bias + ReLU + 2x2 max-pool in the conv epilogue, and its unpool backward, against the
+    separate kernels (bit-identical by construction: same rounding point, same first-maximum rule)."""
+    ops = _ops()
+    x, w, b = _conv_case(N, H, W, Cin, Cout, seed=5)
+    y = ops.conv3x3_fprop(x, w, b, relu=True)
+    p_ref = ops.maxpool2x2(y)
+    p, mask = ops.conv3x3_fprop_pool(x, w, b)
+    assert torch.equal(p, p_ref)
+    dp = bf(torch.randn(N, H // 2, W // 2, Cout, device=DEV))
+    cs_ref = torch.zeros(Cout, device=DEV)
+    dz_ref = ops.maxpool2x2_relu_bwd(y, dp, colsum=cs_ref)
+    cs = torch.zeros(Cout, device=DEV)
+    dz = ops.unpool2x2(dp, mask, colsum=cs)
+    assert torch.equal(dz, dz_ref)
+    assert rel_err(cs, cs_ref) < 1e-3
+
+
 def test_maxpool_fwd_bwd():
     ops = _ops()
     torch.manual_seed(0)
