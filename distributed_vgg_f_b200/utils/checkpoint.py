@@ -63,7 +63,8 @@ def save_checkpoint(path: str, model, optimizer, epoch: int, args: Optional[dict
 
 def load_checkpoint(path: str, model, optimizer=None) -> int:
     """Restore model (+ optimizer) and return the epoch to resume *after*."""
-    payload = torch.load(path, map_location="cpu", weights_only=False)
+    # our files hold tensors and plain containers only: no need to unpickle arbitrary objects
+    payload = torch.load(path, map_location="cpu", weights_only=True)
     state = payload["model"] if "model" in payload else payload
     if hasattr(model, "import_state"):
         model.import_state(strip_module_prefix(state))
