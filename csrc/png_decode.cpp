@@ -49,6 +49,7 @@ static bool decode_one(const std::string& path, PngImage& out) {
     const uint8_t* data = &buf[pos + 8];
     if (pos + 12 + len > buf.size()) return false;
     if (!memcmp(type, "IHDR", 4)) {
+      if (len < 13) return false;
       w = be32(data); h = be32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12];
     } else if (!memcmp(type, "PLTE", 4)) {
       plte.assign(data, data + len);
@@ -59,7 +60,7 @@ static bool decode_one(const std::string& path, PngImage& out) {
     }
     pos += 12 + len;
   }
-  if (w <= 0 || h <= 0 || depth != 8 || interlace != 0) return false;
+  if (w <= 0 || h <= 0 || w > 16384 || h > 16384 || depth != 8 || interlace != 0) return false;
   int ch;
   switch (ctype) {
     case 0: ch = 1; break;
@@ -124,7 +125,11 @@ void decode_png_files(const std::vector<std::string>& paths, int threads, std::v
     for (;;) {
       const size_t i = next.fetch_add(1);
       if (i >= paths.size()) return;
-      decode_one(paths[i], out[i]);
+      try {
+        decode_one(paths[i], out[i]);
+      } catch (...) {            // e.g. bad_alloc on a corrupt header: report "not handled", PIL decides
+        out[i] = PngImage();
+      }
     }
   };
   if (threads < 1) threads = 1;

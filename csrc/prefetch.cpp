@@ -129,7 +129,12 @@ class BatchPrefetcher {
       {
         std::unique_lock<std::mutex> lk(mu_);
         cv_free_.wait(lk, [this] { return !free_.empty() || quit_; });
-        if (quit_) return;
+        if (quit_) {                      // stopped mid-epoch: a consumer blocked in next() must wake up
+          done_ = true;
+          lk.unlock();
+          cv_ready_.notify_all();
+          return;
+        }
         slot = free_.front();
         free_.pop_front();
         ev = events_[slot];

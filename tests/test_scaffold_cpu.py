@@ -397,3 +397,28 @@ def test_weighted_loss_readout_matches_torch():
         n += b
     avg, acc = m.snapshot()
     assert abs(avg.sum - expect) < 1e-5 and avg.count == n and acc.count == n
+
+
+def test_native_png_decoder_rejects_corrupt_files(tmp_path):
+    """Truncated / corrupt / non-PNG files must come back as "not handled" (None), never crash."""
+    from PIL import Image
+
+    from distributed_vgg_f_b200 import ops
+
+    if not ops.available():
+        pytest.skip("native extension not built")
+    good = tmp_path / "good.png"
+    Image.new("RGB", (16, 16), (1, 2, 3)).save(good)
+    raw = good.read_bytes()
+    cases = {"truncated.png": raw[:40], "header_only.png": raw[:8], "garbage.png": b"not a png at all" * 4,
+             "short_ihdr.png": raw[:8] + b"\x00\x00\x00\x00IHDR" + b"\x00" * 4,
+             "huge_dims.png": raw[:16] + b"\x7f\xff\xff\xff\x7f\xff\xff\xff" + raw[24:],
+             "bad_zlib.png": raw[:60] + bytes(len(raw) - 60)}
+    paths = []
+    for name, data in cases.items():
+        (tmp_path / name).write_bytes(data)
+        paths.append(str(tmp_path / name))
+    paths.append(str(tmp_path / "missing.png"))
+    assert ops.native_decode_pngs(paths, 2) is None                 # nothing usable -> caller falls back
+    ok = ops.native_decode_pngs([str(good)], 1)
+    assert ok is not None and tuple(ok.shape) == (1, 16, 16, 3) and int(ok[0, 0, 0, 2]) == 3
