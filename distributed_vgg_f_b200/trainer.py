@@ -25,6 +25,22 @@ from .data.loader import FusedBatch
 from .utils.metrics import DeviceMeter
 
 
+def _bf16_peak() -> float:
+    """Sustained bf16 TFLOP/s of this machine as measured by the driver, else the B200 fallback."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        for key in ("bf16_tflops_sustained", "cublas_bf16_tflops_sustained", "bf16_tflops"):
+            if key in d:
+                return float(d[key])
+    except (OSError, ValueError):
+        pass
+    return 1405.9
+
+
 def _is_native(model) -> bool:
     return hasattr(model, "train_step") and hasattr(model, "eval_step")
 
@@ -64,13 +80,23 @@ class Trainer:
                 flush=True,
             )
             if self.verbose_throughput and train_loss.count:
-                print("[Perf] Epoch: {}/{}, train images/sec (this rank): {:.1f}".format(
-                    epoch, epochs, train_loss.count / max(t1 - t0, 1e-9)), flush=True)
+                print("[Perf] Epoch: {}/{}, train images/sec (this rank): {:.1f}{}".format(
+                    epoch, epochs, train_loss.count / max(t1 - t0, 1e-9),
+                    self._utilisation(train_loss.count, t1 - t0)), flush=True)
             self.history.append(dict(epoch=epoch, train_loss=train_loss.average,
                                      train_acc=train_acc.accuracy, test_loss=test_loss.average,
                                      test_acc=test_acc.accuracy))
             if self.on_epoch_end is not None:
                 self.on_epoch_end(epoch, self)
+
+    def _utilisation(self, images: int, seconds: float) -> str:
+        """Native engine only: achieved training TFLOP/s (3 x forward FLOPs of the layer table) and
+        its fraction of the measured bf16 peak (MEASURED_PEAKS.json next to the package, if any)."""
+        spec, hw = getattr(self.model, "spec", None), getattr(self.model, "HW", None)
+        if not _is_native(self.model) or spec is None or not hw or seconds <= 0:
+            return ""
+        tflops = 3.0 * spec.flops_per_image(hw) * images / seconds / 1e12
+        return ", {:.0f} TFLOP/s ({:.0f}% of the measured bf16 peak)".format(tflops, 100.0 * tflops / _bf16_peak())
 
     # ------------------------------------------------------------------------------------------
     def _to_device(self, batch):

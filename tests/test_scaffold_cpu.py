@@ -422,3 +422,30 @@ def test_native_png_decoder_rejects_corrupt_files(tmp_path):
     assert ops.native_decode_pngs(paths, 2) is None                 # nothing usable -> caller falls back
     ok = ops.native_decode_pngs([str(good)], 1)
     assert ok is not None and tuple(ok.shape) == (1, 16, 16, 3) and int(ok[0, 0, 0, 2]) == 3
+
+
+def test_perf_line_reports_utilisation_for_native_engines():
+    from distributed_vgg_f_b200.models.vggf import vggf_spec
+    from distributed_vgg_f_b200.trainer import Trainer, _bf16_peak
+
+    spec = vggf_spec(3)
+    assert abs(spec.flops_per_image(224) / 1e9 - 30.94) < 0.05
+
+    class FakeEngine:                       # quacks like NativeEngine for Trainer
+        HW = 224
+
+        def __init__(self):
+            self.spec = spec
+
+        def train_step(self, batch):
+            pass
+
+        def eval_step(self, batch):
+            pass
+
+    tr = Trainer(FakeEngine(), None, [], [], torch.device("cpu"), verbose_throughput=True)
+    text = tr._utilisation(images=9340, seconds=1.0)                    # the round-1 single-GPU rate
+    assert "TFLOP/s" in text and "% of the measured bf16 peak" in text
+    tflops = float(text.split(",")[1].split()[0])
+    assert abs(tflops - 3 * 30.94e9 * 9340 / 1e12) < 1.0 and 1000 < _bf16_peak() < 2500
+    assert Trainer(torch.nn.Linear(2, 2), None, [], [], torch.device("cpu"))._utilisation(10, 1.0) == ""
