@@ -12,6 +12,7 @@
 #include "api.h"
 #include "conv0.cuh"
 #include "conv_halo.cuh"
+#include "conv_halo_tma.cuh"
 #include "wgrad_halo.cuh"
 #include "umma_policies.cuh"
 
@@ -171,6 +172,66 @@ static void conv_halo_launch(ConvParams& prm, const bf16* act, cudaStream_t stre
   check_last("conv_halo_kernel launch");
 }
 
+// EXPERIMENTAL (B200_HALO_TMA_EPI=1, not yet run on hardware): halo kernel whose epilogue goes
+// through a shared-memory staging tile and TMA (conv_halo_tma.cuh).  Returns false when the layer's
+// rings + staging do not fit in shared memory: the caller then uses the regular halo kernel.
+static bool halo_tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_HALO_TMA_EPI");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
+template <int BN, bool DGRAD>
+static bool conv_halo_tma_launch(ConvParams& prm, const bf16* act, cudaStream_t stream) {
+  constexpr int B_SLOT = BN * 128;
+  constexpr int MAX_SMEM = 227 * 1024;
+  ConvTile& t = prm.t;
+  t.Wb = HALO_WT; t.Hb = HALO_HT; t.Nb = 1; t.wb_shift = 3; t.hb_shift = 4;
+  t.tiles_w = t.W / HALO_WT; t.tiles_h = t.H / HALO_HT;
+  t.div_tw = make_fastdiv(t.tiles_w); t.div_th = make_fastdiv(t.tiles_h);
+  prm.tiles_m = t.tiles_w * t.tiles_h * t.N;
+  prm.div_tm = make_fastdiv(prm.tiles_m);
+  const int tiles_n = (prm.Cn + BN - 1) / BN;
+  prm.num_tiles = prm.tiles_m * tiles_n;
+  const int cch = prm.Ca / UMMA_BK;
+  const bool masked = DGRAD && prm.mask_src != nullptr;
+  const int budget = MAX_SMEM - halo_tma_smem<BN, DGRAD>(0, 0, masked);
+  ConvTmaExtra ext;
+  if (tiles_n == 1 && 9 * cch <= HALO_TMA_MAX_NB && 9 * cch * B_SLOT + 2 * HALO_SLOT <= budget) {
+    prm.resident = 1;
+    ext.nb = 9 * cch;
+    ext.na = (budget - ext.nb * B_SLOT) / HALO_SLOT;
+  } else {
+    prm.resident = 0;
+    ext.na = 3;
+    ext.nb = (budget - ext.na * HALO_SLOT) / B_SLOT;
+  }
+  if (ext.na > HALO_TMA_MAX_NA) ext.na = HALO_TMA_MAX_NA;
+  if (ext.nb > HALO_TMA_MAX_NB) ext.nb = HALO_TMA_MAX_NB;
+  if (ext.na < 2 || ext.nb < 2) return false;
+  map_nhwc_box(&prm.mapA, act, t.N, t.H, t.W, prm.Ca, HALO_PITCH, HALO_HT + 2, 1);
+  map_nhwc(&ext.mapOut, prm.out, t.N, t.H, t.W, prm.Cn, HALO_WT, HALO_HT, 1);
+  if (masked) map_nhwc(&ext.mapMask, prm.mask_src, t.N, t.H, t.W, prm.Cn, HALO_WT, HALO_HT, 1);
+  else ext.mapMask = ext.mapOut;
+  const int smem = halo_tma_smem<BN, DGRAD>(ext.na, ext.nb, masked);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_tma_kernel<BN, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         MAX_SMEM);
+    if (e != cudaSuccess)
+      throw std::runtime_error(std::string("[b200] cudaFuncSetAttribute(halo tma): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid(prm.num_tiles < num_sms() ? prm.num_tiles : num_sms());
+  conv_halo_tma_kernel<BN, DGRAD><<<grid, UMMA_THREADS, smem, stream>>>(prm, ext);
+  count_launch();
+  check_last("conv_halo_tma_kernel launch");
+  return true;
+}
+
 // ------------------------------------------------------------------------- first conv (no im2col)
 template <bool WGRAD>
 static void conv0_launch(Conv0Params& prm, int grid, cudaStream_t stream) {
@@ -304,6 +365,10 @@ static void fprop_impl(const bf16* x, const bf16* w, const float* bias, bf16* y,
   prm.resident = 0;
   map_2d(&prm.mapB, w, Cout, 9LL * Cin, 9LL * Cin, 64, bn);
   const bool pool = pool_out != nullptr;
+  if (halo_applicable(H, W) && halo_tma_enabled() && !pool && bn <= 128) {
+    if (bn == 64 ? conv_halo_tma_launch<64, false>(prm, x, stream) : conv_halo_tma_launch<128, false>(prm, x, stream))
+      return;
+  }
   if (halo_applicable(H, W)) {
     switch (bn) {
       case 64: pool ? conv_halo_launch<64, false, true>(prm, x, stream) : conv_halo_launch<64, false>(prm, x, stream); return;
@@ -356,6 +421,10 @@ void conv3x3_dgrad(const bf16* dz, const bf16* w, const bf16* mask_src, bf16* dx
   bn = auto_bn(Cin, bn);
   prm.resident = 0;
   map_2d(&prm.mapB, w, Cout, 9LL * Cin, 9LL * Cin, 64, 64);   // MN-major: 64 ci x 64 co boxes
+  if (halo_applicable(H, W) && halo_tma_enabled() && bn <= 128) {
+    if (bn == 64 ? conv_halo_tma_launch<64, true>(prm, dz, stream) : conv_halo_tma_launch<128, true>(prm, dz, stream))
+      return;
+  }
   if (halo_applicable(H, W)) {
     switch (bn) {
       case 64: conv_halo_launch<64, true>(prm, dz, stream); return;
