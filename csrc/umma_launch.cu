@@ -15,6 +15,7 @@
 #include "conv_halo_tma.cuh"
 #include "wgrad_halo.cuh"
 #include "umma_policies.cuh"
+#include "umma_core_dyn.cuh"
 
 namespace b200 {
 
@@ -89,10 +90,63 @@ static int num_sms() {
   return n;
 }
 
+// EXPERIMENTAL (B200_DYNAMIC_TILES=1, not yet run on hardware): dynamic tile scheduler, see
+// umma_core_dyn.cuh.  64 device counters used round-robin; a counter is never reset -- the host
+// tracks how far every launch advances it (num_tiles claims + one over-claim per CTA).
+static bool dynamic_tiles_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_DYNAMIC_TILES");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
+static TileTicket next_ticket(int num_tiles, int grid) {
+  constexpr int SLOTS = 64;
+  static unsigned int* counters = nullptr;
+  static unsigned int bases[SLOTS] = {};
+  static unsigned int seq = 0;
+  static int device = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!counters) {
+    if (cudaMalloc(&counters, SLOTS * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(counters, 0, SLOTS * sizeof(unsigned int)) != cudaSuccess)
+      throw std::runtime_error("[b200] tile counters: allocation failed");
+    device = dev;
+  }
+  if (dev != device) throw std::runtime_error("[b200] dynamic tile scheduling supports one device per process");
+  const unsigned int j = seq++ % SLOTS;
+  TileTicket t{counters + j, bases[j]};
+  bases[j] += static_cast<unsigned int>(num_tiles) + static_cast<unsigned int>(grid);
+  return t;
+}
+
+template <class P>
+static void launch_dyn(const typename P::Params& prm, cudaStream_t stream) {
+  dim3 grid(prm.num_tiles < num_sms() ? prm.num_tiles : num_sms());
+  constexpr int smem = umma_smem_bytes<P::BN, P::STAGES>() + (UMMA_DYN_BAR_BYTES - 256) + P::EPI_SMEM;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(umma_kernel_dyn<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess)
+      throw std::runtime_error(std::string("[b200] cudaFuncSetAttribute(dyn): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  umma_kernel_dyn<P><<<grid, UMMA_THREADS, smem, stream>>>(prm, next_ticket(prm.num_tiles, grid.x));
+  count_launch();
+  check_last("umma_kernel_dyn launch");
+}
+
 // Persistent launch: one CTA per SM (or fewer when there are fewer tiles).
 template <class P>
 static void launch(const typename P::Params& prm, cudaStream_t stream) {
   if (prm.num_tiles <= 0) return;
+  if (dynamic_tiles_enabled()) {
+    launch_dyn<P>(prm, stream);
+    return;
+  }
   dim3 grid(prm.num_tiles < num_sms() ? prm.num_tiles : num_sms());
   constexpr int smem = umma_smem_bytes<P::BN, P::STAGES>() + P::EPI_SMEM;
   static bool configured = false;
