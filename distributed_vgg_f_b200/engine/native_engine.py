@@ -22,7 +22,6 @@ from __future__ import annotations
 
 import os
 
-import math
 from typing import Dict, List, Optional, Tuple
 
 import torch

@@ -16,7 +16,7 @@ The ``Collective`` is ``TorchCollective`` (gloo on CPU -- BASELINE config #1) or
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 import torch.distributed as dist
