@@ -5,6 +5,7 @@
 // Average = sample-weighted loss mean (distributedUtil.py:55-58), torch.optim.Adam with default
 // betas/eps (distributedVggf.py:230).  The reference pays two host syncs per step for the metrics;
 // here they are three atomics into a device meter.
+#include <cstdlib>
 #include <stdexcept>
 
 #include "api.h"
@@ -145,7 +146,16 @@ void adam_fused(float* p, float* m, float* v, const float* g32, const bf16* g16,
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
   const long long n4 = n / 4;
-  const int blocks = static_cast<int>(n4 / 256 + 1 < 148 * 8 ? n4 / 256 + 1 : 148 * 8);
+  // The update runs on the side stream under the persistent conv kernels: how many of its CTAs sit
+  // on an SM decides how much register space a late-starting conv CTA finds.
+  // Tunable without a rebuild: B200_ADAM_CTAS_PER_SM (default 8).
+  static const int per_sm = [] {
+    const char* e = getenv("B200_ADAM_CTAS_PER_SM");
+    const int v = e ? atoi(e) : 8;
+    return v >= 1 && v <= 16 ? v : 8;
+  }();
+  const long long cap = 148LL * per_sm;
+  const int blocks = static_cast<int>(n4 / 256 + 1 < cap ? n4 / 256 + 1 : cap);
   adam_kernel<<<blocks, 256, 0, s>>>(p, m, v, g32, g16, shadow, n4, lr, beta1, beta2, eps, weight_decay,
                                      static_cast<float>(1.0 / bc1), static_cast<float>(1.0 / sqrt(bc2)),
                                      grad_scale, g32_to_zero);

@@ -132,7 +132,9 @@ class NativeEngine:
         self.arena = None
         self.cross_group = None          # inter-node stage of the hierarchical reduction
         self.comm_mode = "single" if self.world == 1 else ("nccl" if self.use_nccl else "flat")
-        self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)
+        # high priority by default: a ready bucket should start reducing at once.  B200_COMM_PRIORITY=0
+        # lets the comm / optimizer CTAs yield to the conv kernels instead.
+        self.comm_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("B200_COMM_PRIORITY", "-1")))
         if self.world > 1 and not self.use_nccl:
             from ..parallel import topology
             from ..parallel.symm import SymmetricArena
