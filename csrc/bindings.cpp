@@ -313,6 +313,23 @@ static void allreduce(const PyComm& comm, c10::optional<at::Tensor> grad, c10::o
   b200::allreduce_fused(comm.c, f32p_opt(grad), f32p_opt(grad_out), start, n, (float)inv_world, (int)algo,
                         wire_fp32, (int)slot, (uint32_t)epoch, (int)max_ctas, cur_stream());
 }
+// EXPERIMENTAL (--zero1): fused reduce-scatter + Adam on the owned cells + all-gather of bf16 weights
+static void zero1_step(const PyComm& comm, c10::optional<at::Tensor> grad, at::Tensor p, at::Tensor m, at::Tensor v,
+                       at::Tensor shadow, int64_t start, int64_t n, double inv_world, int64_t algo, int64_t slot,
+                       int64_t epoch, int64_t max_ctas, double lr, double beta1, double beta2, double eps,
+                       double weight_decay, int64_t step) {
+  TORCH_CHECK(p.scalar_type() == at::kFloat && m.scalar_type() == at::kFloat && v.scalar_type() == at::kFloat &&
+                  shadow.scalar_type() == at::kBFloat16 && p.numel() == m.numel() && p.numel() == v.numel() &&
+                  p.numel() == shadow.numel() && start + n <= p.numel(),
+              "zero1_step: full fp32 arenas (p, m, v) and the bf16 shadow of the same length");
+  b200::zero1_step(comm.c, grad.has_value() ? grad->data_ptr<float>() : nullptr, p.data_ptr<float>(),
+                   m.data_ptr<float>(), v.data_ptr<float>(), bfp_mut(shadow), start, n, (float)inv_world, (int)algo,
+                   (int)slot, (uint32_t)epoch, (int)max_ctas, (float)lr, (float)beta1, (float)beta2, (float)eps,
+                   (float)weight_decay, (int)step, cur_stream());
+}
+static int64_t allreduce_grid(int64_t n, int64_t world, int64_t max_ctas, bool wire_fp32) {
+  return b200::allreduce_grid(n, (int)world, (int)max_ctas, wire_fp32);
+}
 static void broadcast(const PyComm& comm, at::Tensor data, int64_t root, int64_t slot, int64_t epoch) {
   b200::broadcast_fused(comm.c, f32p(data), data.numel(), (int)root, (int)slot, (uint32_t)epoch, cur_stream());
 }
@@ -358,6 +375,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   py::class_<PyComm>(m, "Comm");
   m.def("make_comm", &make_comm);
   m.def("allreduce", &allreduce);
+  m.def("zero1_step", &zero1_step);
+  m.def("allreduce_grid", &allreduce_grid);
   m.def("broadcast", &broadcast);
   m.def("barrier", &barrier);
   m.def("allreduce_signal_words", &b200::allreduce_signal_words);

@@ -122,6 +122,13 @@ enum AllreduceAlgo : int { AR_ONESHOT = 0, AR_TWOSHOT = 1, AR_NVLS = 2 };
 void allreduce_fused(const CommCtx& ctx, const float* grad_f32, float* grad_out_f32,
                      long long start, long long n, float inv_world, int algo, bool wire_fp32,
                      int slot, uint32_t epoch, int max_ctas, cudaStream_t s);
+// CTAs allreduce_fused / zero1_step use for a range of n elements (the cell decomposition follows).
+int allreduce_grid(long long n, int world, int max_ctas, bool wire_fp32);
+// EXPERIMENTAL: ZeRO-1 step of arena range [start, start+n) in one kernel -- reduce-scatter, Adam on
+// the cells this rank owns, all-gather of the new bf16 weights into every rank's shadow (allreduce.cu).
+void zero1_step(const CommCtx& ctx, float* grad_f32, float* p, float* m, float* v, bf16* shadow,
+                long long start, long long n, float inv_world, int algo, int slot, uint32_t epoch, int max_ctas,
+                float lr, float beta1, float beta2, float eps, float weight_decay, int step, cudaStream_t s);
 // Parameter broadcast rank `root` -> all through the wire buffer (K-BCAST).
 void broadcast_fused(const CommCtx& ctx, float* data_f32, long long n, int root, int slot,
                      uint32_t epoch, cudaStream_t s);

@@ -90,6 +90,9 @@ def build_parser() -> argparse.ArgumentParser:
     ext.add_argument("--synthetic", type=int, default=0,
                      help="generate a synthetic ImageFolder with this many train images per class "
                           "under --root_dir if it does not exist")
+    ext.add_argument("--zero1", action="store_true",
+                     help="EXPERIMENTAL: shard the Adam state across the ranks of one NVLink domain -- "
+                          "reduce-scatter + optimizer + all-gather of the new bf16 weights in one kernel")
     ext.add_argument("--reference-order", action="store_true",
                      help="replay the reference's identical-shuffle-every-epoch behaviour")
     ext.add_argument("--shard-eval", action="store_true",

@@ -87,7 +87,7 @@ class NativeEngine:
                  bucket_mb: float = 32.0, seed: int = 0, pretrained_state: Optional[dict] = None,
                  profile: Optional[str] = None, input_hw: int = DATA.crop, comm_ctas: int = 16,
                  init_state: Optional[Dict[str, torch.Tensor]] = None, unpack_fp32: bool = False,
-                 distributed: bool = True) -> None:
+                 distributed: bool = True, zero1: bool = False) -> None:
         ops.require()
         if compute_dtype != "bf16":
             raise NotImplementedError("the native engine computes in bf16 with fp32 master weights; "
@@ -173,6 +173,15 @@ class NativeEngine:
                     for i in ids:
                         self._bucket_prepacked[i] = True
 
+        # EXPERIMENTAL (--zero1): buckets that take a reduce-scatter algorithm run reduce-scatter +
+        # Adam on the owned cells + all-gather of the new bf16 weights as ONE kernel; the fp32 master
+        # and moments of a cell are then only current on its owner (prepare_export gathers them).
+        self.zero1 = bool(zero1) and self.arena is not None and self.arena.wire_dtype == BF16 \
+            and self.cross_group is None and optimizer == "adam"
+        if zero1 and not self.zero1 and self.world > 1:
+            raise ValueError("--zero1 needs Adam, the bf16 wire and all ranks in one NVLink domain")
+        self._zero1_buckets: set = set()
+
         self._build_buffers()
 
     # ============================================================================ parameters
@@ -189,6 +198,22 @@ class NativeEngine:
             ops.require().cast_to_bf16(self.p32, self.w16)
         if sync and self.world > 1:
             self._broadcast_params()
+
+    def prepare_export(self) -> None:
+        """Collective.  Under --zero1 every rank holds the current fp32 master / moments only for the
+        cells it owns: sum the owned pieces over ranks so that every rank has the full state again."""
+        if not self._zero1_buckets:
+            return
+        self.sync()
+        for arena in (self.p32, self.m32, self.v32):
+            for bi in sorted(self._zero1_buckets):
+                bk = self.plan.buckets[bi]
+                tmp = torch.zeros(bk.end - bk.start, dtype=F32, device=self.device)
+                for a, b in self.arena.owned_ranges(bk.start, bk.end - bk.start, self.comm_ctas):
+                    tmp[a - bk.start:b - bk.start] = arena[a:b]
+                dist.all_reduce(tmp)
+                arena[bk.start:bk.end] = tmp
+        torch.cuda.synchronize(self.device)
 
     def export_state(self) -> Dict[str, torch.Tensor]:
         return {name: L.to_torch(self.spec, name, self._view(self.p32, name)).detach().cpu()
@@ -526,6 +551,13 @@ class NativeEngine:
             prepacked = self._bucket_prepacked[bi]
             if prepacked and algo == "oneshot":
                 algo = "twoshot"                 # one-shot cannot leave its result on the wire
+            if self.zero1 and self.apply_updates and algo != "oneshot":
+                self.arena.zero1_step(None if prepacked else self.g32, self.p32, self.m32, self.v32, self.w16,
+                                      s, e - s, algo=algo, slot=bi % self.arena.slots, max_ctas=self.comm_ctas,
+                                      inv_world=1.0 / self.world, lr=self.lr, beta1=self.beta1, beta2=self.beta2,
+                                      eps=self.eps, weight_decay=self.weight_decay, step=self.step_count)
+                self._zero1_buckets.add(bi)
+                return
             to_f32 = (algo == "oneshot" or self.unpack_fp32 or self.arena.wire_dtype == F32
                       or not self.apply_updates)
             self.arena.allreduce(None if prepacked else self.g32, self.g32 if to_f32 else None, s, e - s,

@@ -20,6 +20,22 @@ from .. import ops
 ONESHOT_MAX_BYTES = 512 * 1024      # wire bytes below which the latency-optimal one-shot wins
 
 
+def owned_cells(start: int, n: int, G: int, world: int, rank: int):
+    """The cell decomposition of csrc/allreduce.cu in Python: the bucket is cut into G chunks of
+    ``world`` cells of ``cell`` 8-element vectors; cell (b, r) is reduced (and, under ZeRO-1, owned)
+    by rank r.  Returns [(first element, one past the last element)] for ``rank``."""
+    nvec = n // 8
+    cell = (nvec + G * world - 1) // (G * world)
+    out = []
+    for b in range(G):
+        chunk0, chunk1 = min(nvec, b * world * cell), min(nvec, (b + 1) * world * cell)
+        c0 = min(chunk1, chunk0 + rank * cell)
+        c1 = min(chunk1, c0 + cell)
+        if c1 > c0:
+            out.append((start + 8 * c0, start + 8 * c1))
+    return out
+
+
 class SymmetricArena:
     def __init__(self, wire_elems: int, device: torch.device, wire_dtype: torch.dtype = torch.bfloat16,
                  slots: int = 32, group=None) -> None:
@@ -80,6 +96,24 @@ class SymmetricArena:
                                 self._algo[algo], self.wire_dtype == torch.float32, slot,
                                 self.next_epoch(slot), max_ctas)
         return algo
+
+    def zero1_step(self, grad_f32: Optional[torch.Tensor], p32: torch.Tensor, m32: torch.Tensor,
+                   v32: torch.Tensor, w16: torch.Tensor, start: int, n: int, *, algo: str, slot: int,
+                   max_ctas: int, inv_world: float, lr: float, beta1: float, beta2: float, eps: float,
+                   weight_decay: float, step: int) -> None:
+        """EXPERIMENTAL: reduce-scatter + Adam on the cells this rank owns + all-gather of the new
+        bf16 weights, one kernel (csrc/allreduce.cu::zero1_kernel).  bf16 wire, two-shot or NVLS."""
+        if self.wire_dtype != torch.bfloat16 or algo not in ("twoshot", "nvls"):
+            raise ValueError("zero1_step needs the bf16 wire and a reduce-scatter algorithm")
+        ops.require().zero1_step(self.comm, grad_f32, p32, m32, v32, w16, start, n, inv_world,
+                                 self._algo[algo], slot, self.next_epoch(slot), max_ctas, lr, beta1, beta2,
+                                 eps, weight_decay, step)
+
+    def owned_ranges(self, start: int, n: int, max_ctas: int):
+        """Element ranges of [start, start+n) whose fp32 master this rank owns under zero1_step
+        (cell (b, r) of the kernel's decomposition belongs to rank r)."""
+        G = int(ops.require().allreduce_grid(n, self.world, max_ctas, False))
+        return owned_cells(start, n, G, self.world, self.rank)
 
     def broadcast_(self, data_f32: torch.Tensor, root: int = 0, slot: int = 0) -> None:
         """Rank ``root``'s fp32 ``data`` -> every rank, pulled through the wire buffer in chunks."""

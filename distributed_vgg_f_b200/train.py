@@ -81,7 +81,8 @@ def manage_training(args) -> Trainer:
                              optimizer=args.optimizer, momentum=args.momentum,
                              compute_dtype=args.dtype, allreduce=args.allreduce,
                              wire_dtype=args.wire_dtype, bucket_mb=args.bucket_mb, seed=args.seed,
-                             pretrained_state=pretrained, profile=args.profile)
+                             pretrained_state=pretrained, profile=args.profile,
+                             zero1=getattr(args, "zero1", False))
         optimizer = None            # fused into the engine
     else:
         model = build_oracle(spec, seed=args.seed, pretrained_state=pretrained).to(device)

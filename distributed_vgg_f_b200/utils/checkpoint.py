@@ -50,6 +50,8 @@ def optimizer_state(model, optimizer) -> Dict[str, Any]:
 
 def save_checkpoint(path: str, model, optimizer, epoch: int, args: Optional[dict] = None,
                     is_rank0: bool = True) -> None:
+    if hasattr(model, "prepare_export"):     # collective: engines with sharded optimizer state gather it
+        model.prepare_export()
     if not is_rank0:
         return
     payload = {"format": FORMAT, "model": model_state(model),

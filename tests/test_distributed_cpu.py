@@ -160,3 +160,20 @@ def test_hierarchy_groups_gloo_world4():
     import torch.multiprocessing as mp
 
     mp.spawn(_topology_worker, args=(4, _free_port()), nprocs=4, join=True)
+
+
+def test_zero1_cell_ownership_partitions_the_bucket():
+    """parallel.symm.owned_cells mirrors the kernel's decomposition (csrc/allreduce.cu): over all ranks
+    the owned ranges tile the bucket exactly once, in 8-element units."""
+    from distributed_vgg_f_b200.parallel.symm import owned_cells
+
+    for start, n, G, world in [(0, 8, 1, 2), (2048, 8 * 1000, 4, 8), (8 * 37, 8 * 123457, 16, 8), (0, 8 * 5, 16, 4),
+                               (4096, 102_764_544, 16, 8)]:
+        covered = []
+        for r in range(world):
+            cells = owned_cells(start, n, G, world, r)
+            assert all((a - start) % 8 == 0 and (b - start) % 8 == 0 and b > a for a, b in cells)
+            covered += cells
+        covered.sort()
+        assert covered[0][0] == start and covered[-1][1] == start + n
+        assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))     # no gap, no overlap
