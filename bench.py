@@ -151,7 +151,8 @@ def run_native(args):
     spec = get_spec(args.model, args.num_classes)
     eng = NativeEngine(spec, device=device, batch=args.batch, lr=1e-5, optimizer=args.optimizer,
                        allreduce=args.allreduce, wire_dtype=args.wire_dtype, bucket_mb=args.bucket_mb,
-                       seed=0, input_hw=args.hw, comm_ctas=args.comm_ctas)
+                       seed=0, input_hw=args.hw, comm_ctas=args.comm_ctas,
+                       zero1=args.zero1 and world > 1)
     host = make_host_batches(torch, 4, args.batch, args.num_classes, seed=rank + 1)
     dev_batches = [FusedBatch(b.images_u8.to(device), b.params.to(device), b.labels.to(device), b.resized_hw, None)
                    for b in host]
@@ -223,7 +224,8 @@ def run_native(args):
             "data": "synthetic 128x128 RGB uint8 images -> fused GPU augment -> 224x224; random-init weights",
             "config": {"model": args.model, "num_classes": args.num_classes, "global_batch": gb,
                        "per_gpu_batch": args.batch, "input": "%dx%d" % (args.hw, args.hw), "seq_len": None,
-                       "parallelism": "dp%d" % world, "optimizer": args.optimizer,
+                       "parallelism": ("dp%d+zero1" if getattr(eng, "zero1", False) else "dp%d") % world,
+                       "optimizer": args.optimizer,
                        "allreduce": args.allreduce, "wire_dtype": args.wire_dtype,
                        "l2_policy": "per-step working set (activations+weights, >2 GB) exceeds the 126 MB L2; "
                                     "4 distinct input batches rotated"},
@@ -356,6 +358,7 @@ def main():
     ap.add_argument("--bucket-mb", type=float, default=32.0)
     ap.add_argument("--comm-ctas", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--zero1", action="store_true", help="experimental fused ZeRO-1 step (docs/EXPERIMENTAL.md)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

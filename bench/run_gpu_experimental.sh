@@ -19,3 +19,13 @@ bench default "B200_NOP=1"
 run pool "B200_EXPERIMENTAL=1" "fprop_pool_fused" && bench pool "B200_FUSE_POOL=1"
 run tmaepi "B200_HALO_TMA_EPI=1" "conv_fprop or conv_dgrad or engine or backward or train" && bench tmaepi "B200_HALO_TMA_EPI=1"
 run dyntiles "B200_DYNAMIC_TILES=1" "gemm or conv or engine or backward or train" && bench dyntiles "B200_DYNAMIC_TILES=1"
+# the fused ZeRO-1 step needs >= 2 GPUs (gpurun --gpus 2 ...):
+if [ "$(python -c 'import torch; print(torch.cuda.device_count())')" -ge 2 ]; then
+  B200_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_multigpu.py -x -q -m gpu -k zero1 > gpurun_out/exp_zero1_pytest.log 2>&1
+  echo "== zero1 pytest exit $?: $(tail -n 1 gpurun_out/exp_zero1_pytest.log | cut -c1-120)"
+  N=$(python -c 'import torch; print(torch.cuda.device_count())')
+  for z in "" "--zero1"; do
+    timeout 300 python bench.py --gpus $N --steps 30 --warmup 5 $z > gpurun_out/exp_zero1_bench${z:+_on}.log 2>&1
+    echo "== N=$N bench ${z:-default}: $(grep '^{' gpurun_out/exp_zero1_bench${z:+_on}.log | cut -c1-200)"
+  done
+fi
