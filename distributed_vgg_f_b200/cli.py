@@ -59,7 +59,11 @@ def build_parser() -> argparse.ArgumentParser:
                         help="Mini-batch size. The default value is {}".format(TRAIN.mini_batch))
 
     ext = parser.add_argument_group("extensions (not in the reference)")
-    ext.add_argument("--model", default="vggf", choices=["vggf", "vgg16", "vggf-tiny", "vggf-mini"])
+    ext.add_argument("--model", default="vggf",
+                     choices=["vggf", "vgg16", "vgg11", "vgg13", "vgg19", "vggf11", "vggf13", "vggf19",
+                              "vggf-tiny", "vggf-mini"],
+                     help="vggf = the reference's network (VGG-16 + funnel head); vggNN = torchvision's plain "
+                          "VGG-NN; vggfNN = VGG-NN + funnel head; -tiny / -mini are test-sized")
     ext.add_argument("--num-classes", type=int, default=None,
                      help="override the class count (default: number of class folders)")
     ext.add_argument("--engine", default="auto", choices=["auto", "native", "oracle"],
@@ -90,6 +94,8 @@ def build_parser() -> argparse.ArgumentParser:
     ext.add_argument("--synthetic", type=int, default=0,
                      help="generate a synthetic ImageFolder with this many train images per class "
                           "under --root_dir if it does not exist")
+    ext.add_argument("--eval-only", action="store_true",
+                     help="one validation pass (typically with --resume <checkpoint>) and exit")
     ext.add_argument("--zero1", action="store_true",
                      help="EXPERIMENTAL: shard the Adam state across the ranks of one NVLink domain -- "
                           "reduce-scatter + optimizer + all-gather of the new bf16 weights in one kernel")

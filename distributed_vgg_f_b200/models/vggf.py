@@ -89,9 +89,19 @@ class VGGSpec:
         return total
 
 
-def _conv_specs(width_div: int = 1) -> tuple:
+# torchvision's other plain VGG depths (configurations A, B, E of the paper; VGG16_CFG is D).  The
+# reference only ever builds VGG-16; these come for free from the layer table: same kernels, same
+# state-dict keys as torchvision.models.vgg11 / vgg13 / vgg19, with or without the funnel head.
+VGG_CFGS = {
+    11: [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+    13: [64, 64, "M", 128, 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+    19: [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"],
+}
+
+
+def _conv_specs(width_div: int = 1, cfg_list=None) -> tuple:
     convs, cin, idx = [], 3, 0
-    cfg = [v if v == "M" else max(int(v) // width_div, 8) for v in VGG16_CFG]
+    cfg = [v if v == "M" else max(int(v) // width_div, 8) for v in (cfg_list or VGG16_CFG)]
     for i, v in enumerate(cfg):
         if v == "M":
             idx += 1
@@ -124,6 +134,16 @@ def vgg16_spec(num_classes: int = 1000) -> VGGSpec:
         FCSpec("classifier.6", 4096, num_classes, False, 0.0),
     )
     return VGGSpec(_conv_specs(), fcs, num_classes)
+
+
+def vgg_spec(depth: int, num_classes: int = 1000, funnel: bool = False) -> VGGSpec:
+    """torchvision VGG-11 / 13 / 16 / 19 (no batch norm), optionally with the reference's funnel head."""
+    if depth == 16:
+        return vggf_spec(num_classes) if funnel else vgg16_spec(num_classes)
+    if depth not in VGG_CFGS:
+        raise ValueError("VGG depth must be 11, 13, 16 or 19")
+    head = vggf_spec(num_classes).fcs if funnel else vgg16_spec(num_classes).fcs
+    return VGGSpec(_conv_specs(1, VGG_CFGS[depth]), head, num_classes)
 
 
 def vggf_tiny_spec(num_classes: int) -> VGGSpec:
@@ -161,7 +181,12 @@ def get_spec(model: str, num_classes: int) -> VGGSpec:
         return vggf_spec(num_classes)
     if model in ("vgg16", "vgg-16"):
         return vgg16_spec(num_classes)
-    raise ValueError("unknown model %r (expected 'vggf' or 'vgg16')" % model)
+    for depth in (11, 13, 19):
+        if model in ("vgg%d" % depth, "vgg-%d" % depth):
+            return vgg_spec(depth, num_classes)
+        if model in ("vggf%d" % depth, "vgg%d-funnel" % depth):
+            return vgg_spec(depth, num_classes, funnel=True)
+    raise ValueError("unknown model %r (vggf, vgg16, vgg11/13/19, vggf11/13/19, vggf-mini, vggf-tiny)" % model)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -122,5 +122,10 @@ def manage_training(args) -> Trainer:
             raise ValueError("--class-weights needs %d comma-separated values" % num_classes)
     trainer = Trainer(model, optimizer, train_loader, valid_loader, device, class_weights=cw,
                       on_epoch_end=on_epoch_end, shard_eval=getattr(args, "shard_eval", False))
+    if getattr(args, "eval_only", False):        # score a checkpoint: one validation pass, no training
+        test_loss, test_acc = trainer._evaluate()
+        print("[Info] Evaluation: test loss: {}, test acc: {}.".format(test_loss, test_acc), flush=True)
+        trainer.history.append(dict(epoch=start_epoch - 1, test_loss=test_loss.average, test_acc=test_acc.accuracy))
+        return trainer
     trainer.fit(args.epochs, start_epoch=start_epoch)
     return trainer

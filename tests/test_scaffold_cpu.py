@@ -449,3 +449,45 @@ def test_perf_line_reports_utilisation_for_native_engines():
     tflops = float(text.split(",")[1].split()[0])
     assert abs(tflops - 3 * 30.94e9 * 9340 / 1e12) < 1.0 and 1000 < _bf16_peak() < 2500
     assert Trainer(torch.nn.Linear(2, 2), None, [], [], torch.device("cpu"))._utilisation(10, 1.0) == ""
+
+
+@pytest.mark.parametrize("depth,params", [(11, 132_863_336), (13, 133_047_848), (19, 143_667_240)])
+def test_other_vgg_depths_match_torchvision(depth, params):
+    """VGG-11/13/19 from the same layer table: torchvision's parameter count, state-dict keys and
+    forward (the native engine executes the table; the oracle is checked here)."""
+    import torchvision
+
+    from distributed_vgg_f_b200.models.vggf import build_oracle, get_spec, vgg_spec
+
+    spec = vgg_spec(depth, 1000)
+    assert spec.num_params == params
+    assert get_spec("vgg%d" % depth, 1000).num_params == params
+    funnel = get_spec("vggf%d" % depth, 3)
+    assert [f.name for f in funnel.fcs][-2:] == ["classifier.6.0", "classifier.6.3"] and funnel.fcs[-1].fout == 3
+    if depth != 11:
+        return                                             # one full forward is enough for CI time
+    tv = getattr(torchvision.models, "vgg%d" % depth)(weights=None).eval()
+    ours = build_oracle(spec, seed=0).eval()
+    assert list(tv.state_dict().keys()) == list(ours.state_dict().keys())
+    ours.load_state_dict(tv.state_dict())
+    x = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        assert torch.allclose(tv(x), ours(x), rtol=1e-5, atol=1e-6)
+
+
+def test_eval_only_scores_a_checkpoint(synth_root, tmp_path, capsys):
+    """--save then --resume --eval-only reproduces the validation line of the training run."""
+    import re
+
+    from distributed_vgg_f_b200.cli import parse_command_line
+    from distributed_vgg_f_b200.train import manage_training
+
+    ck = str(tmp_path / "ck.pt")
+    base = ["-iu", "tcp://127.0.0.1:1", "-rn", "0", "-ws", "1", "-rd", synth_root, "-nc", "-mb", "4",
+            "--model", "vggf-tiny", "--engine", "oracle"]
+    manage_training(parse_command_line(base + ["-ep", "1", "--save", ck]))
+    trained = re.search(r"test loss: ([\d.]+), test acc: ([\d.]+)%", capsys.readouterr().out).groups()
+    manage_training(parse_command_line(base + ["--resume", ck, "--eval-only"]))
+    out = capsys.readouterr().out
+    assert "[Info] Evaluation:" in out and "Epoch:" not in out.split("[Info] Evaluation:")[1]
+    assert re.search(r"Evaluation: test loss: ([\d.]+), test acc: ([\d.]+)%", out).groups() == trained
