@@ -491,3 +491,27 @@ def test_eval_only_scores_a_checkpoint(synth_root, tmp_path, capsys):
     out = capsys.readouterr().out
     assert "[Info] Evaluation:" in out and "Epoch:" not in out.split("[Info] Evaluation:")[1]
     assert re.search(r"Evaluation: test loss: ([\d.]+), test acc: ([\d.]+)%", out).groups() == trained
+
+
+def test_predict_tool_reproduces_validation_accuracy(synth_root, tmp_path, capsys):
+    """tools/predict on the validation folder gives the accuracy the training run printed."""
+    import re
+
+    from distributed_vgg_f_b200.cli import parse_command_line
+    from distributed_vgg_f_b200.tools import predict as P
+    from distributed_vgg_f_b200.train import manage_training
+
+    ck = str(tmp_path / "ck.pt")
+    manage_training(parse_command_line(["-iu", "tcp://127.0.0.1:1", "-rn", "0", "-ws", "1", "-rd", synth_root, "-nc",
+                                        "-mb", "4", "-ep", "1", "--model", "vggf-tiny", "--engine", "oracle",
+                                        "--pipeline", "reference", "--save", ck]))
+    acc = float(re.search(r"test acc: ([\d.]+)%", capsys.readouterr().out).group(1))
+    val = os.path.join(synth_root, "ValidationData")
+    logits, files = P.predict(ck, [val], engine="oracle")
+    classes = sorted(os.listdir(val))
+    truth = torch.tensor([classes.index(os.path.basename(os.path.dirname(f))) for f in files])
+    assert logits.shape == (len(files), 3)
+    assert abs(100.0 * float((logits.argmax(1) == truth).float().mean()) - acc) < 0.01      # printed with 2 decimals
+    assert P.main([ck, files[0], "--classes", "edible,other,toy", "--engine", "oracle"]) == 0
+    line = capsys.readouterr().out.strip().split("\t")
+    assert line[0] == files[0] and line[1] in ("edible", "other", "toy") and 0.0 < float(line[2]) <= 1.0
