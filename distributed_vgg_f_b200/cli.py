@@ -130,12 +130,21 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     from .train import manage_training
 
     args = parse_command_line(argv)
+    from .parallel.process_group import shutdown
+    from .parallel.watchdog import start_abort_watch
+
+    watch = start_abort_watch(args.rank)          # None for single-process runs
     try:
         manage_training(args)
-    finally:
-        from .parallel.process_group import shutdown
-
-        shutdown()
+    except BaseException as e:                    # tell the peers before going down (they may be
+        if watch is not None:                     # blocked in a collective this rank will never join)
+            watch.signal("%s: %s" % (type(e).__name__, e))
+            watch.stop()
+        shutdown(graceful=False)
+        raise
+    if watch is not None:
+        watch.stop()
+    shutdown()
     return 0
 
 

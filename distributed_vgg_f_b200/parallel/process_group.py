@@ -60,8 +60,12 @@ def init_distributed(init_url: Optional[str], rank_: int, world_size_: int, devi
     dist.init_process_group(**kwargs)
 
 
-def shutdown() -> None:
+def shutdown(graceful: bool = True) -> None:
+    """Leave the job.  ``graceful=False`` (this rank failed): no barrier -- the peers are not going to
+    reach one -- and no blocking teardown."""
     if distributed_is_initialized():
+        if not graceful:
+            return
         try:
             dist.barrier()
         except Exception:

@@ -177,3 +177,35 @@ def test_zero1_cell_ownership_partitions_the_bucket():
         covered.sort()
         assert covered[0][0] == start and covered[-1][1] == start + n
         assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))     # no gap, no overlap
+
+
+def test_failing_rank_takes_the_job_down_quickly(synth_root, tmp_path):
+    """one rank fails (bad data root) -> every rank exits non-zero within seconds instead of
+    sitting in a collective until the process-group timeout (what the reference does)."""
+    import time
+
+    port = _free_port()
+    t0 = time.time()
+    good = _launch(0, port, synth_root, [])
+    bad = _launch(1, port, str(tmp_path / "does_not_exist"), [])
+    outs = [p.communicate(timeout=120)[0] for p in (good, bad)]
+    assert time.time() - t0 < 90
+    assert bad.returncode != 0 and "FileNotFoundError" in outs[1]
+    assert good.returncode != 0, outs[0][-500:]
+
+
+def test_abort_watch_fires_on_store_key():
+    """The watchdog thread itself: a peer's abort key makes this process exit with status 75."""
+    code = (
+        "import time, datetime, torch.distributed as dist\n"
+        "from distributed_vgg_f_b200.parallel.watchdog import AbortWatch\n"
+        "store = dist.TCPStore('127.0.0.1', %d, 1, True, timeout=datetime.timedelta(seconds=20))\n"
+        "w = AbortWatch(rank=0, interval=0.2, store=store).start()\n"
+        "peer = AbortWatch(rank=1, interval=0.2, store=store)\n"
+        "peer.signal('ValueError: boom')\n"
+        "time.sleep(10)\n"
+        "print('still alive')\n" % _free_port())
+    p = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT),
+                       capture_output=True, text=True, timeout=60)
+    assert p.returncode == 75, (p.returncode, p.stdout, p.stderr[-500:])
+    assert "a peer failed -- rank 1: ValueError: boom" in p.stderr and "still alive" not in p.stdout
