@@ -94,6 +94,9 @@ def build_parser() -> argparse.ArgumentParser:
     ext.add_argument("--synthetic", type=int, default=0,
                      help="generate a synthetic ImageFolder with this many train images per class "
                           "under --root_dir if it does not exist")
+    ext.add_argument("--socket-ifname", default=None,
+                     help="network interface for the rendezvous / gloo / NCCL bootstrap sockets (the reference "
+                          "hard-codes GLOO_SOCKET_IFNAME=eth0, distributedVggf.py:296; default: auto-detect)")
     ext.add_argument("--eval-only", action="store_true",
                      help="one validation pass (typically with --resume <checkpoint>) and exit")
     ext.add_argument("--zero1", action="store_true",
@@ -118,6 +121,9 @@ def parse_command_line(argv: Optional[Sequence[str]] = None, init: bool = True):
     if args.root_dir is None:
         build_parser().error("the following arguments are required: -rd/--root_dir")
     print(args)
+    if args.socket_ifname:
+        os.environ["GLOO_SOCKET_IFNAME"] = args.socket_ifname
+        os.environ.setdefault("NCCL_SOCKET_IFNAME", args.socket_ifname)
     if init and args.world_size > 1:
         from .parallel.process_group import init_distributed, pick_device
 
