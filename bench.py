@@ -167,6 +167,13 @@ def run_native(args):
     ms, _ = timed_region(torch, dist, world, device,
                          lambda k: eng.train_step(dev_batches[k % len(dev_batches)]), args.steps)
     launches = ops.launch_count() - l0
+    # gradient all-reduce as the step sees it (events on the comm stream; outside the timed region)
+    ar_steps = min(args.steps, 10)
+    eng.comm_timing(True)
+    for k in range(ar_steps):
+        eng.train_step(dev_batches[k % len(dev_batches)])
+    ar_report = eng.comm_report(ar_steps)
+    eng.comm_timing(False)
 
     # end-to-end through the public API: DataManager (decoded uint8 cache -> pinned batch ring filled
     # by the prefetch thread) -> engine.train_step(batch): every step copies its inputs host->device
@@ -234,6 +241,7 @@ def run_native(args):
                     "api": "DataManager(ImageFolder on disk, decoded uint8 cache, pinned ring) -> "
                            "NativeEngine.train_step(batch) + async loss read-back"},
             "gpu_launches": int(launches), "clocks": clk,
+            "allreduce": ar_report,
             "final_loss": float(loss_host[-1]),
         }
         print(json.dumps(out), flush=True)
@@ -356,7 +364,7 @@ def main():
     ap.add_argument("--allreduce", default="auto")
     ap.add_argument("--wire-dtype", default="bf16")
     ap.add_argument("--bucket-mb", type=float, default=32.0)
-    ap.add_argument("--comm-ctas", type=int, default=16)
+    ap.add_argument("--comm-ctas", type=int, default=48)
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--zero1", action="store_true", help="experimental fused ZeRO-1 step (docs/EXPERIMENTAL.md)")
     args = ap.parse_args()

@@ -48,20 +48,26 @@ def main():
         dist.all_reduce(tmp16[:n])
         out[:n].copy_(tmp16[:n])                                # decompress
 
+    cta_list = [int(c) for c in os.environ.get("AR_CTAS", "8,16,32,48,64,96,128").split(",")]
     for n in sizes:
         iters = 50 if n <= (1 << 22) else (20 if n <= (1 << 26) else 8)
         row = {"fp32_bytes": n * 4, "wire_bytes": n * 2}
         for algo in algos:
-            if algo == "oneshot" and n > (1 << 24):
+            if algo == "oneshot" and n > (1 << 22):
                 continue
-            for ctas in ((16, 32, 64) if n >= (1 << 22) else (16,)):
-                ms = timed(lambda: arena.allreduce(grad, out, 0, n, algo=algo, slot=1, max_ctas=ctas), iters)
+            for ctas in (cta_list if n >= (1 << 18) else (cta_list[0], cta_list[-1])):
+                # (a) what a conv bucket does: pack fp32 -> wire, reduce, Adam reads the wire (no unpack)
+                fn = (lambda: arena.allreduce(grad, out, 0, n, algo=algo, slot=1, max_ctas=ctas)) if algo == "oneshot" \
+                    else (lambda: arena.allreduce(grad, None, 0, n, algo=algo, slot=1, max_ctas=ctas))
+                ms = timed(fn, iters)
                 key = "%s_c%d" % (algo, ctas)
                 row[key + "_us"] = ms * 1e3
                 row[key + "_busGBs"] = 2 * (world - 1) / world * n * 2 / (ms * 1e-3) / 1e9
-            if algo != "oneshot":
-                ms = timed(lambda: arena.allreduce(grad, None, 0, n, algo=algo, slot=2, max_ctas=32), iters)
-                row[algo + "_nounpack_c32_us"] = ms * 1e3
+                if algo != "oneshot":
+                    # (b) what an FC-weight bucket does: the wgrad GEMM already wrote the wire (no pack, no unpack)
+                    ms = timed(lambda: arena.allreduce(None, None, 0, n, algo=algo, slot=2, max_ctas=ctas), iters)
+                    row[key + "_wireonly_us"] = ms * 1e3
+                    row[key + "_wireonly_busGBs"] = 2 * (world - 1) / world * n * 2 / (ms * 1e-3) / 1e9
         ms = timed(lambda: nccl_arm(n), iters)
         row["nccl_bf16_hook_us"] = ms * 1e3
         row["nccl_busGBs"] = 2 * (world - 1) / world * n * 2 / (ms * 1e-3) / 1e9

@@ -28,10 +28,24 @@
 
 namespace b200 {
 
-constexpr int AR_MAX_CTAS = 64;
+// Footprint: the comm stream's CTAs run WHILE the persistent tcgen05 conv kernels of backward hold
+// every SM (one 320-thread CTA of up to 168 registers = 53 760 of the SM's 65 536 registers, all of
+// its shared memory).  A 256-thread CTA capped at 40 registers (10 240) and no shared memory fits
+// next to any of them, so a reduction CTA never waits for an SM and a conv CTA never waits for a
+// reduction: the link is saturated by MANY thin CTAs (bytes in flight = CTAs x 256 threads x UNR x
+// 16 B) instead of a few fat ones that evict the convolution from 16 SMs (round 1: 512 threads x 64
+// registers, +0.73 ms per step at every world size).
+constexpr int AR_MAX_CTAS = 128;
 constexpr int AR_MAX_WORLD = 16;
-constexpr int AR_THREADS = 512;
+constexpr int AR_THREADS = 256;
+constexpr int AR_MIN_BLOCKS = 6;                                // __launch_bounds__ -> <= 40 registers
 constexpr int AR_SLOT_WORDS = 2 * AR_MAX_CTAS * AR_MAX_WORLD;   // two phases per slot
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ uint32_t* flag_ptr(uint32_t* pad, int slot, int phase, int cta, int src) {
   return pad + ((static_cast<long long>(slot) * 2 + phase) * AR_MAX_CTAS + cta) * AR_MAX_WORLD + src;
@@ -46,12 +60,20 @@ __device__ __forceinline__ void cta_barrier_all_ranks(const CommCtx& c, int slot
     fence_acq_rel_sys();
     st_release_sys(flag_ptr(c.signal_ptrs[peer], slot, phase, cta, c.rank), epoch);
     const uint32_t* mine = flag_ptr(c.signal_ptrs[c.rank], slot, phase, cta, peer);
-    unsigned long long spins = 0;
+    // Bounded by WALL CLOCK (%globaltimer), not by a spin count: a peer may legitimately be late by
+    // seconds (rank 0 writing a checkpoint, a slow first batch) -- the limit is minutes and
+    // configurable (B200_BARRIER_TIMEOUT_S), and only a genuinely dead peer trips it.
+    unsigned int spins = 0;
+    unsigned long long t0 = 0;
     while (static_cast<int>(ld_acquire_sys(mine) - epoch) < 0) {
-      if (++spins > (1ull << 25)) {
-        printf("[b200] cross-GPU barrier timeout rank=%d peer=%d slot=%d phase=%d cta=%d epoch=%u seen=%u\n",
-               c.rank, peer, slot, phase, cta, epoch, ld_relaxed_sys(mine));
-        __trap();
+      if ((++spins & 1023u) == 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > c.timeout_ns) {
+          printf("[b200] cross-GPU barrier timeout rank=%d peer=%d slot=%d phase=%d cta=%d epoch=%u seen=%u\n",
+                 c.rank, peer, slot, phase, cta, epoch, ld_relaxed_sys(mine));
+          __trap();
+        }
       }
     }
   }
@@ -90,7 +112,7 @@ struct ArArgs {
 
 // One 16-byte wire vector = 8 bf16 (WIRE32 = false) or 4 fp32 (WIRE32 = true).
 template <int ALGO, bool WIRE32>
-__global__ void __launch_bounds__(AR_THREADS, 1) allreduce_kernel(const ArArgs a) {
+__global__ void __launch_bounds__(AR_THREADS, AR_MIN_BLOCKS) allreduce_kernel(const ArArgs a) {
   constexpr int EPV = WIRE32 ? 4 : 8;                 // elements per vector
   const CommCtx& c = a.c;
   const int b = blockIdx.x, G = gridDim.x, world = c.world, rank = c.rank;
@@ -101,21 +123,22 @@ __global__ void __launch_bounds__(AR_THREADS, 1) allreduce_kernel(const ArArgs a
   uint8_t* my_wire = reinterpret_cast<uint8_t*>(c.wire_ptrs[rank]) + a.start * (WIRE32 ? 4 : 2);
 
   // ---- pack: fp32 arena -> wire (scaled, rounded once) -----------------------------------------
-  constexpr int UNR = 4;        // independent 16-byte transactions in flight per thread
+  constexpr int UNR = 4;        // independent 16-byte wire transactions in flight per thread
+  constexpr int PUNR = 2;       // pack: 2 x 32 fp32 bytes in flight per thread (register budget)
   if (a.grad) {
     const float* g = a.grad + a.start;
     const float s = a.inv_world;
     long long v = chunk0 + threadIdx.x;
     if constexpr (!WIRE32) {
-      for (; v + (UNR - 1) * AR_THREADS < chunk1; v += UNR * AR_THREADS) {
-        float4 x0[UNR], x1[UNR];
+      for (; v + (PUNR - 1) * AR_THREADS < chunk1; v += PUNR * AR_THREADS) {
+        float4 x0[PUNR], x1[PUNR];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
+        for (int u = 0; u < PUNR; ++u) {
           x0[u] = *reinterpret_cast<const float4*>(g + (v + u * AR_THREADS) * 8);
           x1[u] = *reinterpret_cast<const float4*>(g + (v + u * AR_THREADS) * 8 + 4);
         }
 #pragma unroll
-        for (int u = 0; u < UNR; ++u)
+        for (int u = 0; u < PUNR; ++u)
           st_v4(my_wire + (v + u * AR_THREADS) * 16,
                 make_uint4(pack_bf16x2(x0[u].x * s, x0[u].y * s), pack_bf16x2(x0[u].z * s, x0[u].w * s),
                            pack_bf16x2(x1[u].x * s, x1[u].y * s), pack_bf16x2(x1[u].z * s, x1[u].w * s)));
@@ -179,8 +202,21 @@ __global__ void __launch_bounds__(AR_THREADS, 1) allreduce_kernel(const ArArgs a
         res = make_uint4(__float_as_uint(acc.x), __float_as_uint(acc.y), __float_as_uint(acc.z), __float_as_uint(acc.w));
       } else {
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int p = 0; p < world; ++p) {
-          const int peer = (rank + p) % world;
+        int p = 0;
+        for (; p + 4 <= world; p += 4) {          // four peer loads in flight, then accumulate
+          uint4 r4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            int peer = rank + p + u;
+            if (peer >= world) peer -= world;
+            r4[u] = ld_v4(reinterpret_cast<const uint8_t*>(c.wire_ptrs[peer]) + boff);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) accum_bf16x8(acc, r4[u]);
+        }
+        for (; p < world; ++p) {
+          int peer = rank + p;
+          if (peer >= world) peer -= world;
           accum_bf16x8(acc, ld_v4(reinterpret_cast<const uint8_t*>(c.wire_ptrs[peer]) + boff));
         }
         res = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
@@ -252,7 +288,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) allreduce_kernel(const ArArgs a
 // buckets).  Exposed so that the host can reproduce which rank owns which cell (zero1_step).
 int allreduce_grid(long long n, int world, int max_ctas, bool wire_fp32) {
   const long long nvec = n / (wire_fp32 ? 4 : 8);
-  int G = max_ctas <= 0 ? 16 : max_ctas;
+  int G = max_ctas <= 0 ? 48 : max_ctas;
   if (G > AR_MAX_CTAS) G = AR_MAX_CTAS;
   const long long want = nvec / (static_cast<long long>(AR_THREADS) * world) + 1;
   if (want < G) G = static_cast<int>(want);

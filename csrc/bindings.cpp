@@ -1,5 +1,6 @@
 // pybind11 surface of the native library: adapts torch tensors to the raw-pointer API of api.h.
 // Every op runs on torch's current CUDA stream of the tensor's device.
+#include <cstdlib>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
@@ -305,6 +306,11 @@ static PyComm make_comm(int64_t rank, int64_t world, int64_t wire_ptrs_dev, int6
   p.c.signal_ptrs = reinterpret_cast<uint32_t* const*>(signal_ptrs_dev);
   p.c.wire_mc = reinterpret_cast<void*>(wire_mc);
   p.c.signal_mc = reinterpret_cast<uint32_t*>(signal_mc);
+  // cross-GPU waits are bounded by wall clock; minutes by default so that host-side skew (rank 0
+  // writing a checkpoint, a slow loader) never trips it -- only a dead peer does
+  double secs = 600.0;
+  if (const char* e = std::getenv("B200_BARRIER_TIMEOUT_S")) secs = std::atof(e) > 0 ? std::atof(e) : secs;
+  p.c.timeout_ns = static_cast<unsigned long long>(secs * 1e9);
   return p;
 }
 static void allreduce(const PyComm& comm, c10::optional<at::Tensor> grad, c10::optional<at::Tensor> grad_out,

@@ -112,6 +112,7 @@ struct CommCtx {
   uint32_t* const* signal_ptrs;  // device array [world]: peers' signal pads
   void* wire_mc;                 // multicast alias of the wire buffer (NVLS) or nullptr
   uint32_t* signal_mc;           // multicast alias of the signal pad or nullptr
+  unsigned long long timeout_ns; // wall-clock bound of every cross-GPU wait (B200_BARRIER_TIMEOUT_S)
 };
 enum AllreduceAlgo : int { AR_ONESHOT = 0, AR_TWOSHOT = 1, AR_NVLS = 2 };
 // Fused gradient all-reduce of arena range [start, start+n):

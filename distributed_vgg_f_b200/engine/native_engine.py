@@ -85,9 +85,10 @@ class NativeEngine:
                  optimizer: str = "adam", momentum: float = TRAIN.momentum, weight_decay: float = 0.0,
                  compute_dtype: str = "bf16", allreduce: str = "auto", wire_dtype: str = "bf16",
                  bucket_mb: float = 32.0, seed: int = 0, pretrained_state: Optional[dict] = None,
-                 profile: Optional[str] = None, input_hw: int = DATA.crop, comm_ctas: int = 16,
+                 profile: Optional[str] = None, input_hw: int = DATA.crop, comm_ctas: int = 48,
                  init_state: Optional[Dict[str, torch.Tensor]] = None, unpack_fp32: bool = False,
-                 distributed: bool = True, zero1: bool = False) -> None:
+                 distributed: bool = True, zero1: bool = False, conv_bucket_mb: float = 9.5,
+                 tail_bucket_kb: float = 2400.0, same_dropout_all_ranks: bool = False) -> None:
         ops.require()
         if compute_dtype != "bf16":
             raise NotImplementedError("the native engine computes in bf16 with fp32 master weights; "
@@ -101,12 +102,14 @@ class NativeEngine:
         self.lr, self.opt_name, self.momentum, self.weight_decay = lr, optimizer, momentum, weight_decay
         self.beta1, self.beta2, self.eps = TRAIN.adam_beta1, TRAIN.adam_beta2, TRAIN.adam_eps
         self.seed, self.HW = int(seed), int(input_hw)
+        self.same_dropout_all_ranks = bool(same_dropout_all_ranks)
         self.step_count = 0
         self.train_dropout = True        # tests switch dropout off to compare gradients exactly
         self.apply_updates = True        # False: leave raw gradients in g32 (gradient inspection)
         self.meter: Optional[DeviceMeter] = None
         self.class_weights: Optional[torch.Tensor] = None
         self.timer = PhaseTimer(profile == "events", nvtx=(profile == "nvtx"))
+        self._comm_events: Optional[list] = None     # [(start, end, wire bytes)] while comm timing is on
         self.nvtx = profile == "nvtx"
         self.world = dist.get_world_size() if (distributed and distributed_is_initialized()) else 1
         self.rank = dist.get_rank() if (distributed and distributed_is_initialized()) else 0
@@ -115,8 +118,15 @@ class NativeEngine:
         dev = self.device
 
         # ---- flat arenas (gradient-ready order) --------------------------------------------------
+        # FC weights (ready first, 88 % of the bytes): ``bucket_mb`` messages.  Convolution gradients
+        # (ready one layer at a time over the rest of backward): one bucket per big layer, and a small
+        # final bucket -- its reduction and update are the only exposed part of the exchange.
         cap = int(bucket_mb * 1024 * 1024 / 4)
-        self.plan: BucketPlan = make_bucket_plan(L.ready_order(spec), cap_elems=cap)
+        order = L.ready_order(spec)
+        first_conv = next((n for n, _ in order if n.startswith("features.")), "")
+        self.plan: BucketPlan = make_bucket_plan(
+            order, cap_elems=cap, late_cap_elems=min(cap, int(conv_bucket_mb * 1024 * 1024 / 4)),
+            late_from=first_conv, tail_elems=int(tail_bucket_kb * 1024 / 4))
         n = self.plan.total
         self.p32 = torch.zeros(n, dtype=F32, device=dev)
         self.g32 = torch.zeros(n, dtype=F32, device=dev)
@@ -231,6 +241,8 @@ class NativeEngine:
 
     def import_optimizer_state(self, st: dict) -> None:
         self.step_count = int(st.get("step", 0))
+        if "lr" in st:                       # a run resumed behind an LR-step boundary keeps the decayed rate
+            self.lr = float(st["lr"])
         with torch.no_grad():
             for key, arena in (("exp_avg", self.m32), ("exp_avg_sq", self.v32), ("momentum_buffer", self.m32)):
                 if key in st and arena is not None:
@@ -270,7 +282,7 @@ class NativeEngine:
         # EXPERIMENTAL, off unless B200_FUSE_POOL=1: the pooled layers' conv epilogue pools in
         # registers and records argmax / ReLU bit masks; the un-pooled activation is never written
         # (acts[i] of such a layer then holds stale data) and backward is an "unpool" kernel.
-        want_fused_pool = os.environ.get("B200_FUSE_POOL", "0") == "1"
+        want_fused_pool = os.environ.get("B200_FUSE_POOL", "1") == "1"
         self.pool_masks: List[Optional[torch.Tensor]] = []
         h = HW
         for i, c in enumerate(spec.convs):
@@ -358,6 +370,13 @@ class NativeEngine:
     def _b(self, name: str) -> torch.Tensor:
         return self._view(self.p32, name + ".bias")
 
+    def _drop_key(self, layer: int) -> int:
+        """Philox key of a dropout layer.  Every replica draws its OWN mask, like the reference's
+        per-process RNG (distributedVggf.py:55; one process per rank) -- identical masks on all ranks
+        would correlate the replicas' gradient noise.  ``same_dropout_all_ranks`` is for parity tests."""
+        r = 0 if self.same_dropout_all_ranks else self.rank
+        return self.seed * 1000003 + layer + 7919 * r
+
     @staticmethod
     def _ksplit(m_tiles: int, k_iters: int, target: int = 256) -> int:
         return max(1, min(k_iters, target // max(m_tiles, 1)))
@@ -401,7 +420,7 @@ class NativeEngine:
             else:
                 p = f.dropout if (train and self.train_dropout) else 0.0
                 ops.fc_bias_act(acc, self._b(f.name), self.fc_y[i][:b], None, B=b, N=f.fout, relu=f.relu,
-                                drop_p=p, seed=self.seed * 1000003 + i, offset=self.step_count)
+                                drop_p=p, seed=self._drop_key(i), offset=self.step_count)
                 h = self.fc_y[i][:b]
 
     # ============================================================================== backward
@@ -551,7 +570,11 @@ class NativeEngine:
             prepacked = self._bucket_prepacked[bi]
             if prepacked and algo == "oneshot":
                 algo = "twoshot"                 # one-shot cannot leave its result on the wire
-            if self.zero1 and self.apply_updates and algo != "oneshot":
+            # ZeRO-1 only for buckets that hold nothing but one big FC weight (88 % of the parameters):
+            # the forward pass reads those through the all-gathered bf16 shadow.  Buckets with biases
+            # stay replicated -- biases are read from the fp32 master, which under ZeRO-1 is current on
+            # the owner rank only.
+            if self.zero1 and self.apply_updates and prepacked and algo != "oneshot":
                 self.arena.zero1_step(None if prepacked else self.g32, self.p32, self.m32, self.v32, self.w16,
                                       s, e - s, algo=algo, slot=bi % self.arena.slots, max_ctas=self.comm_ctas,
                                       inv_world=1.0 / self.world, lr=self.lr, beta1=self.beta1, beta2=self.beta2,
@@ -560,9 +583,17 @@ class NativeEngine:
                 return
             to_f32 = (algo == "oneshot" or self.unpack_fp32 or self.arena.wire_dtype == F32
                       or not self.apply_updates)
+            ev0 = None
+            if self._comm_events is not None:    # observability: device time of every reduction
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
             self.arena.allreduce(None if prepacked else self.g32, self.g32 if to_f32 else None, s, e - s,
                                  algo=algo, slot=bi % self.arena.slots, max_ctas=self.comm_ctas,
                                  inv_world=1.0 / self.world)
+            if ev0 is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
+                self._comm_events.append((ev0, ev1, (e - s) * self.arena.wire.element_size()))
             if self.cross_group is not None:     # node sums (already x 1/world) -> job sum, over NCCL
                 dist.all_reduce(self.g32[s:e] if to_f32 else self.arena.wire[s:e], group=self.cross_group)
             if self.apply_updates:
@@ -622,6 +653,29 @@ class NativeEngine:
 
     def sync(self) -> None:
         torch.cuda.synchronize(self.device)
+
+    # ---- gradient all-reduce observability (GB/s and roofline fraction) -----------------
+    def comm_timing(self, on: bool) -> None:
+        """Record CUDA events around every fused all-reduce launch (comm stream).  The times include
+        whatever the kernel waits for (peers arriving late) and run under backward's kernels -- it is
+        the rate the training step actually sees, not an isolated micro-benchmark."""
+        self._comm_events = [] if on else None
+
+    def comm_report(self, steps: int) -> Optional[dict]:
+        """Device time and bus bandwidth of the gradient all-reduces of the last ``steps`` steps:
+        bus GB/s = 2(ws-1)/ws * wire bytes / time (NCCL's convention), against the measured 770 GB/s
+        peer-copy rate and the nominal 900 GB/s per direction."""
+        if not self._comm_events or self.world == 1:
+            return None
+        self.sync()
+        ms = sum(a.elapsed_time(b) for a, b, _ in self._comm_events)
+        nbytes = sum(n for _, _, n in self._comm_events)
+        self._comm_events = []
+        bus = 2.0 * (self.world - 1) / self.world * nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"wire_MB_per_step": round(nbytes / steps / 1e6, 2), "ms_per_step": round(ms / steps, 4),
+                "launches_per_step": len(self.plan.buckets), "bus_GBs": round(bus, 1),
+                "frac_of_770_measured": round(bus / 770.0, 3), "frac_of_900_nominal": round(bus / 900.0, 3),
+                "comm_ctas": self.comm_ctas, "overlapped_with_backward": True}
 
     def phase_times(self) -> Dict[str, float]:
         return self.timer.collect()

@@ -55,10 +55,21 @@ def _round_up(x: int, m: int) -> int:
 
 
 def make_bucket_plan(ready_order: Sequence[Tuple[str, int]], cap_elems: int = 16 * 1024 * 1024,
-                     first_cap_elems: int = 0, align: int = 2048) -> BucketPlan:
-    """``ready_order``: (name, numel) in the order gradients are produced by backward."""
+                     first_cap_elems: int = 0, align: int = 2048, late_cap_elems: int = 0,
+                     late_from: str = "", tail_elems: int = 0) -> BucketPlan:
+    """``ready_order``: (name, numel) in the order gradients are produced by backward.
+
+    ``late_cap_elems`` / ``late_from``: from tensor ``late_from`` on, buckets are capped at the smaller
+    ``late_cap_elems``.  The big early tensors (the FC weights: 88 % of VGG-F, all ready in the first
+    tenth of backward) want large messages; the convolution gradients trickle in over the rest of
+    backward and the LAST bucket's reduction + optimizer step is the only part of the whole gradient
+    exchange that nothing can hide, so the late buckets are one layer each and the final one is
+    additionally held to ``tail_elems`` (the first convolutions: a few hundred KB, latency-bound).
+    """
     if cap_elems % align:
         cap_elems = _round_up(cap_elems, align)
+    if late_cap_elems and late_cap_elems % align:
+        late_cap_elems = _round_up(late_cap_elems, align)
     offsets, numels, order, pos = {}, {}, [], 0
     for name, n in ready_order:
         offsets[name], numels[name] = pos, n
@@ -75,9 +86,22 @@ def make_bucket_plan(ready_order: Sequence[Tuple[str, int]], cap_elems: int = 16
             buckets.append(Bucket(len(buckets), cur_start, end, tuple(cur_names)))
         cur_start, cur_names = end, []
 
+    # the tail: the longest suffix of the ready order that fits ``tail_elems`` gets its own bucket
+    tail_start = total
+    if tail_elems:
+        for name in reversed(order):
+            if total - offsets[name] > tail_elems:
+                break
+            tail_start = offsets[name]
+    late = False
     for name in order:
         t0, t1 = offsets[name], offsets[name] + _round_up(numels[name], align)
+        late = late or (bool(late_from) and name == late_from)
         cap = first_cap_elems if (first_cap_elems and not buckets) else cap_elems
+        if late and late_cap_elems:
+            cap = late_cap_elems
+        if t0 == tail_start and cur_names:
+            close(t0)
         if (t1 - t0) > cap:
             close(t0)                       # flush what we have, then split the big tensor
             p = t0

@@ -17,7 +17,9 @@ import torch.distributed as dist
 
 from .. import ops
 
-ONESHOT_MAX_BYTES = 512 * 1024      # wire bytes below which the latency-optimal one-shot wins
+ONESHOT_MAX_BYTES = 512 * 1024      # wire bytes below which the latency-optimal one-shot wins (no multicast)
+ONESHOT_MAX_BYTES_NVLS = 64 * 1024  # with NVLS the switch does the ws-way sum: it wins from ~32 KB at ws=8
+                                    # (profiles/r1_v4_allreduce_sweep_ws8.json)
 
 
 def owned_cells(start: int, n: int, G: int, world: int, rank: int):
@@ -80,12 +82,12 @@ class SymmetricArena:
                 raise RuntimeError("NVLS requested but the wire buffer has no multicast mapping")
             return requested
         nbytes = n_elems * self.wire.element_size()
-        if nbytes <= ONESHOT_MAX_BYTES:
+        if nbytes <= (ONESHOT_MAX_BYTES_NVLS if self.has_multicast else ONESHOT_MAX_BYTES):
             return "oneshot"
         return "nvls" if self.has_multicast else "twoshot"
 
     def allreduce(self, grad_f32: Optional[torch.Tensor], grad_out_f32: Optional[torch.Tensor],
-                  start: int, n: int, algo: str = "auto", slot: int = 0, max_ctas: int = 16,
+                  start: int, n: int, algo: str = "auto", slot: int = 0, max_ctas: int = 48,
                   inv_world: Optional[float] = None) -> str:
         """Fused pack + reduce (+ unpack) of arena range [start, start+n) on the current stream."""
         algo = self.pick_algo(n, algo)

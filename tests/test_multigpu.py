@@ -60,7 +60,7 @@ def _allreduce_worker(rank, world, wire_fp32):
                     scaled = scaled.to(torch.bfloat16).float()
                 ref = scaled.clone()
                 dist.all_reduce(ref)
-                used = arena.allreduce(g, out, start, n, algo=algo, slot=it % 4, max_ctas=16)
+                used = arena.allreduce(g, out, start, n, algo=algo, slot=it % 4, max_ctas=(16, 48, 128)[it])
                 assert used == algo
                 torch.cuda.synchronize(dev)
                 got = out[start:start + n]
@@ -128,6 +128,15 @@ def test_engine_data_parallel_equivalence(algo):
     _run(_engine_worker, 2, algo)
 
 
+@pytest.mark.parametrize("world", [4, 8])
+def test_engine_data_parallel_equivalence_wide(world):
+    """The same equivalence (N ranks x batch 4 == one process x batch 4N; replicas identical after an
+    update) at 4 and 8 ranks, default algorithm choice (NVLS where the fabric has multicast)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    _run(_engine_worker, world, "auto")
+
+
 def _hier_worker(rank, world, fake_node_size):
     if fake_node_size:
         os.environ["B200_FAKE_NODE_SIZE"] = str(fake_node_size)
@@ -181,7 +190,7 @@ def _stress_worker(rank, world):
         if skew.random() < 0.5:
             torch.cuda._sleep(int(skew.random() * 3e6))         # up to ~1.5 ms of skew
         m = 8 * plan.randrange(1, n // 8)
-        arena.allreduce(g, out, 0, m, algo=algo, slot=0, max_ctas=plan.choice([1, 4, 16]))
+        arena.allreduce(g, out, 0, m, algo=algo, slot=0, max_ctas=plan.choice([1, 4, 16, 48, 128]))
         expect = (it % 7 + 1) * (world + 1) / 2.0
         torch.cuda.synchronize(dev)
         assert float((out[:m] - expect).abs().max()) < 0.05 * expect, (it, algo)
@@ -190,6 +199,53 @@ def _stress_worker(rank, world):
 
 def test_allreduce_barrier_stress():
     _run(_stress_worker, min(torch.cuda.device_count(), 8))
+
+
+def _stress_slots_worker(rank, world):
+    """200 back-to-back all-reduces that mix bucket sizes (8 elements .. 8 MB), algorithms, CTA counts,
+    pack / wire-only entry AND signal-pad slots, launched from two streams like the engine does
+    (comm stream + the stream that joins it), with random per-rank skew."""
+    import random
+
+    from distributed_vgg_f_b200.parallel.symm import SymmetricArena
+
+    dev = torch.device("cuda", rank)
+    n = 1 << 22
+    arena = SymmetricArena(n, dev)
+    skew = random.Random(4321 + rank)
+    plan = random.Random(7)
+    algos = ["oneshot", "twoshot"] + (["nvls"] if arena.has_multicast else [])
+    side = torch.cuda.Stream(device=dev)
+    sizes = [8, 8 * 31, 4096, 65536 + 8, 1 << 18, (1 << 20) + 8 * 5, 1 << 22]
+    g = torch.empty(n, device=dev)
+    out = torch.zeros(n, device=dev)
+    for it in range(200):
+        algo = plan.choice(algos)
+        m = plan.choice(sizes)
+        start = 2048 * plan.randrange(0, (n - m) // 2048 + 1)
+        slot = plan.randrange(0, arena.slots)
+        ctas = plan.choice([1, 3, 16, 48, 128])
+        wire_only = algo != "oneshot" and plan.random() < 0.4
+        val = float((rank + 1) * (it % 5 + 1))
+        expect = (it % 5 + 1) * (world + 1) / 2.0
+        with torch.cuda.stream(side):
+            if skew.random() < 0.4:
+                torch.cuda._sleep(int(skew.random() * 2e6))
+            if wire_only:             # the producer wrote bf16(g / ws) on the wire itself (FC wgrad epilogue)
+                arena.wire[start:start + m].fill_(val / world)
+                arena.allreduce(None, None, start, m, algo=algo, slot=slot, max_ctas=ctas)
+                got = arena.wire[start:start + m].float()
+            else:
+                g[start:start + m].fill_(val)
+                arena.allreduce(g, out if algo == "oneshot" else None, start, m, algo=algo, slot=slot, max_ctas=ctas)
+                got = out[start:start + m] if algo == "oneshot" else arena.wire[start:start + m].float()
+            bad = float((got - expect).abs().max())
+        torch.cuda.current_stream(dev).wait_stream(side)
+        assert bad < 0.05 * expect, (it, algo, m, slot, ctas, wire_only, bad)
+
+
+def test_allreduce_stress_mixed_slots_200():
+    _run(_stress_slots_worker, min(torch.cuda.device_count(), 8))
 
 
 # ------------------------------------------------------------------- experimental: fused ZeRO-1 step
