@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(AR_THREADS, AR_MIN_BLOCKS) allreduce_kernel(co
         float4 x0[PUNR], x1[PUNR];
 #pragma unroll
         for (int u = 0; u < PUNR; ++u) {
-          x0[u] = *reinterpret_cast<const float4*>(g + (v + u * AR_THREADS) * 8);
-          x1[u] = *reinterpret_cast<const float4*>(g + (v + u * AR_THREADS) * 8 + 4);
+          x0[u] = __ldcs(reinterpret_cast<const float4*>(g + (v + u * AR_THREADS) * 8));      // read once: streaming
+          x1[u] = __ldcs(reinterpret_cast<const float4*>(g + (v + u * AR_THREADS) * 8 + 4));
         }
 #pragma unroll
         for (int u = 0; u < PUNR; ++u)
@@ -365,9 +365,9 @@ __device__ __forceinline__ uint4 zero1_adam8(const Zero1Args& a, long long elem,
   float pp[8], mm[8], vv[8];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const float4 p4 = *reinterpret_cast<const float4*>(a.p + elem + 4 * h);
-    const float4 m4 = *reinterpret_cast<const float4*>(a.m + elem + 4 * h);
-    const float4 v4 = *reinterpret_cast<const float4*>(a.v + elem + 4 * h);
+    const float4 p4 = __ldcs(reinterpret_cast<const float4*>(a.p + elem + 4 * h));   // streaming: see adam_kernel
+    const float4 m4 = __ldcs(reinterpret_cast<const float4*>(a.m + elem + 4 * h));
+    const float4 v4 = __ldcs(reinterpret_cast<const float4*>(a.v + elem + 4 * h));
     pp[4 * h] = p4.x; pp[4 * h + 1] = p4.y; pp[4 * h + 2] = p4.z; pp[4 * h + 3] = p4.w;
     mm[4 * h] = m4.x; mm[4 * h + 1] = m4.y; mm[4 * h + 2] = m4.z; mm[4 * h + 3] = m4.w;
     vv[4 * h] = v4.x; vv[4 * h + 1] = v4.y; vv[4 * h + 2] = v4.z; vv[4 * h + 3] = v4.w;
@@ -382,16 +382,21 @@ __device__ __forceinline__ uint4 zero1_adam8(const Zero1Args& a, long long elem,
   }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    *reinterpret_cast<float4*>(a.p + elem + 4 * h) = make_float4(pp[4 * h], pp[4 * h + 1], pp[4 * h + 2], pp[4 * h + 3]);
-    *reinterpret_cast<float4*>(a.m + elem + 4 * h) = make_float4(mm[4 * h], mm[4 * h + 1], mm[4 * h + 2], mm[4 * h + 3]);
-    *reinterpret_cast<float4*>(a.v + elem + 4 * h) = make_float4(vv[4 * h], vv[4 * h + 1], vv[4 * h + 2], vv[4 * h + 3]);
+    __stcs(reinterpret_cast<float4*>(a.p + elem + 4 * h), make_float4(pp[4 * h], pp[4 * h + 1], pp[4 * h + 2], pp[4 * h + 3]));
+    __stcs(reinterpret_cast<float4*>(a.m + elem + 4 * h), make_float4(mm[4 * h], mm[4 * h + 1], mm[4 * h + 2], mm[4 * h + 3]));
+    __stcs(reinterpret_cast<float4*>(a.v + elem + 4 * h), make_float4(vv[4 * h], vv[4 * h + 1], vv[4 * h + 2], vv[4 * h + 3]));
   }
   return make_uint4(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]), pack_bf16x2(pp[4], pp[5]),
                     pack_bf16x2(pp[6], pp[7]));
 }
 
+// 128 threads x <= 80 registers (the Adam state of 8 parameters lives in registers between the
+// reduce and the broadcast) = 10 240 registers: the same footprint as allreduce_kernel, so these CTAs
+// also co-reside with every conv kernel of backward.
+constexpr int Z1_THREADS = 128;
+constexpr int Z1_MIN_BLOCKS = 6;
 template <int ALGO>
-__global__ void __launch_bounds__(AR_THREADS, 1) zero1_kernel(const Zero1Args a) {
+__global__ void __launch_bounds__(Z1_THREADS, Z1_MIN_BLOCKS) zero1_kernel(const Zero1Args a) {
   static_assert(ALGO == AR_TWOSHOT || ALGO == AR_NVLS, "the owner-computes step needs a reduce-scatter");
   const CommCtx& c = a.c;
   const int b = blockIdx.x, G = gridDim.x, world = c.world, rank = c.rank;
@@ -404,7 +409,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) zero1_kernel(const Zero1Args a)
   if (a.grad) {                         // pack + re-zero the fp32 gradient range for the next step
     float* g = a.grad + a.start;
     const float s = a.inv_world;
-    for (long long v = chunk0 + threadIdx.x; v < chunk1; v += AR_THREADS) {
+    for (long long v = chunk0 + threadIdx.x; v < chunk1; v += Z1_THREADS) {
       const float4 x0 = *reinterpret_cast<const float4*>(g + v * 8);
       const float4 x1 = *reinterpret_cast<const float4*>(g + v * 8 + 4);
       *reinterpret_cast<float4*>(g + v * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -419,12 +424,18 @@ __global__ void __launch_bounds__(AR_THREADS, 1) zero1_kernel(const Zero1Args a)
   const long long cell1 = min(chunk1, cell0 + cell);
   if constexpr (ALGO == AR_NVLS) {
     uint8_t* mc = reinterpret_cast<uint8_t*>(c.wire_mc) + a.start * 2;
-    for (long long v = cell0 + threadIdx.x; v < cell1; v += AR_THREADS) {
-      const uint4 gred = multimem_ld_reduce_bf16x8(mc + v * 16);        // switch adds, fp32 accumulate
+    // software pipeline: the switch reduction of the NEXT vector is in flight while this one's Adam
+    // state (96 bytes of p, m, v) is loaded, updated and stored
+    long long v = cell0 + threadIdx.x;
+    uint4 gnext = make_uint4(0, 0, 0, 0);
+    if (v < cell1) gnext = multimem_ld_reduce_bf16x8(mc + v * 16);       // switch adds, fp32 accumulate
+    for (; v < cell1; v += Z1_THREADS) {
+      const uint4 gred = gnext;
+      if (v + Z1_THREADS < cell1) gnext = multimem_ld_reduce_bf16x8(mc + (v + Z1_THREADS) * 16);
       multimem_st_v4(mc + v * 16, zero1_adam8(a, a.start + v * 8, gred));
     }
   } else {
-    for (long long v = cell0 + threadIdx.x; v < cell1; v += AR_THREADS) {
+    for (long long v = cell0 + threadIdx.x; v < cell1; v += Z1_THREADS) {
       const long long boff = a.start * 2 + v * 16;
       float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       for (int p = 0; p < world; ++p) {
@@ -443,8 +454,8 @@ __global__ void __launch_bounds__(AR_THREADS, 1) zero1_kernel(const Zero1Args a)
   cta_barrier_all_ranks(c, a.slot, 1, b, a.epoch);
 
   bf16* sh = a.shadow + a.start;        // every rank: new weights of the whole chunk -> local shadow
-  for (long long v = chunk0 + threadIdx.x; v < chunk1; v += AR_THREADS)
-    *reinterpret_cast<uint4*>(sh + v * 8) = ld_v4(my_wire + v * 16);
+  for (long long v = chunk0 + threadIdx.x; v < chunk1; v += Z1_THREADS)
+    __stcs(reinterpret_cast<uint4*>(sh + v * 8), ld_v4(my_wire + v * 16));
 }
 
 void zero1_step(const CommCtx& ctx, float* grad_f32, float* p, float* m, float* v, bf16* shadow,
@@ -461,8 +472,8 @@ void zero1_step(const CommCtx& ctx, float* grad_f32, float* p, float* m, float* 
   a.bc1_inv = static_cast<float>(1.0 / (1.0 - pow(static_cast<double>(beta1), step)));
   a.bc2_inv_sqrt = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(beta2), step)));
   const int G = allreduce_grid(n, ctx.world, max_ctas, false);
-  if (algo == AR_NVLS) zero1_kernel<AR_NVLS><<<G, AR_THREADS, 0, s>>>(a);
-  else zero1_kernel<AR_TWOSHOT><<<G, AR_THREADS, 0, s>>>(a);
+  if (algo == AR_NVLS) zero1_kernel<AR_NVLS><<<G, Z1_THREADS, 0, s>>>(a);
+  else zero1_kernel<AR_TWOSHOT><<<G, Z1_THREADS, 0, s>>>(a);
   count_launch();
   check_last("zero1_step");
 }

@@ -128,12 +128,12 @@ void augment_fused(const uint8_t* src, const float* params, bf16* out, int N, in
   for (int c = 0; c < 3; ++c) { g.mean[c] = mean[c]; g.inv_std[c] = 1.f / stdv[c]; }
   const long long pixels = static_cast<long long>(N) * OH * OW;
   if (mode == 0) {
-    const int blocks = static_cast<int>((pixels + 255) / 256 < 148 * 16 ? (pixels + 255) / 256 : 148 * 16);
+    const int blocks = static_cast<int>((pixels + 255) / 256 < sm_count() * 16 ? (pixels + 255) / 256 : sm_count() * 16);
     augment_nhwc_kernel<<<blocks, 256, 0, s>>>(src, params, out, g, pad);
   } else {
     if (pad < 32 || pad % 8) throw std::runtime_error("[b200] augment_fused: kpad must be a multiple of 8, >= 32");
     const long long total = pixels * (pad / 8);
-    const int blocks = static_cast<int>((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    const int blocks = static_cast<int>((total + 255) / 256 < sm_count() * 32 ? (total + 255) / 256 : sm_count() * 32);
     augment_im2col_kernel<<<blocks, 256, 0, s>>>(src, params, out, g, pad);
   }
   count_launch();
@@ -179,7 +179,7 @@ __global__ void im2col3x3_c3_kernel(const bf16* __restrict__ x, bf16* __restrict
 void im2col3x3_c3(const bf16* x, bf16* out, int N, int H, int W, int cpad, int kpad, cudaStream_t s) {
   if (cpad != 4 || kpad % 8 || kpad < 32) throw std::runtime_error("[b200] im2col3x3_c3: cpad must be 4, kpad a multiple of 8 >= 32");
   const long long total = static_cast<long long>(N) * H * W * (kpad / 8);
-  const int blocks = static_cast<int>((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+  const int blocks = static_cast<int>((total + 255) / 256 < sm_count() * 32 ? (total + 255) / 256 : sm_count() * 32);
   im2col3x3_c3_kernel<<<blocks, 256, 0, s>>>(x, out, N, H, W, cpad, kpad);
   count_launch();
   check_last("im2col3x3_c3");
@@ -201,7 +201,7 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, bf16* 
 
 void nchw_f32_to_nhwc_bf16(const float* x, bf16* y, int N, int C, int H, int W, int cpad, cudaStream_t s) {
   const long long total = static_cast<long long>(N) * H * W;
-  const int blocks = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  const int blocks = static_cast<int>((total + 255) / 256 < sm_count() * 16 ? (total + 255) / 256 : sm_count() * 16);
   nchw_f32_to_nhwc_bf16_kernel<<<blocks, 256, 0, s>>>(x, y, N, C, H, W, cpad);
   count_launch();
   check_last("nchw_f32_to_nhwc_bf16");

@@ -67,7 +67,7 @@ __global__ void maxpool2x2_fwd_kernel(const bf16* __restrict__ x, bf16* __restri
 void maxpool2x2_fwd(const bf16* x, bf16* y, int N, int H, int W, int C, cudaStream_t s) {
   if (C % 8 || H % 2 || W % 2) throw std::runtime_error("[b200] maxpool2x2: need C%8==0 and even H,W");
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
-  const int blocks = min(ceil_div_ll(total, 256), 148 * 16);
+  const int blocks = min(ceil_div_ll(total, 256), sm_count() * 16);
   maxpool2x2_fwd_kernel<<<blocks, 256, 0, s>>>(x, y, N, H, W, C);
   count_launch();
   check_last("maxpool2x2_fwd");
@@ -137,7 +137,7 @@ void maxpool2x2_relu_bwd(const bf16* y, const bf16* dp, bf16* dz, float* colsum,
   if (colsum && 256 % (C / 8) != 0)
     throw std::runtime_error("[b200] maxpool2x2_bwd: fused column sum needs C/8 to divide 256");
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
-  const int blocks = min(ceil_div_ll(total, 256), 148 * 16);
+  const int blocks = min(ceil_div_ll(total, 256), sm_count() * 16);
   maxpool2x2_relu_bwd_kernel<<<blocks, 256, colsum ? C * sizeof(float) : 0, s>>>(y, dp, dz, colsum, N, H, W, C);
   count_launch();
   check_last("maxpool2x2_relu_bwd");
@@ -201,7 +201,7 @@ void unpool2x2(const bf16* dp, const uint32_t* mask, bf16* dz, float* colsum, in
   if (colsum && 256 % (C / 8) != 0)
     throw std::runtime_error("[b200] unpool2x2: fused column sum needs C/8 to divide 256");
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
-  const int blocks = min(ceil_div_ll(total, 256), 148 * 16);
+  const int blocks = min(ceil_div_ll(total, 256), sm_count() * 16);
   unpool2x2_kernel<<<blocks, 256, colsum ? C * sizeof(float) : 0, s>>>(dp, mask, dz, colsum, N, H, W, C);
   count_launch();
   check_last("unpool2x2");
@@ -272,7 +272,7 @@ void adaptive_avgpool_fwd(const bf16* x, bf16* y, int N, int H, int W, int C, in
                           cudaStream_t s) {
   if (C % 8) throw std::runtime_error("[b200] adaptive_avgpool: C%8 != 0");
   const long long total = static_cast<long long>(N) * OH * OW * (C / 8);
-  adaptive_avgpool_fwd_kernel<<<min(ceil_div_ll(total, 256), 148 * 16), 256, 0, s>>>(x, y, N, H, W, C, OH, OW);
+  adaptive_avgpool_fwd_kernel<<<min(ceil_div_ll(total, 256), sm_count() * 16), 256, 0, s>>>(x, y, N, H, W, C, OH, OW);
   count_launch();
   check_last("adaptive_avgpool_fwd");
 }
@@ -280,7 +280,7 @@ void adaptive_avgpool_bwd(const bf16* dy, bf16* dx, int N, int H, int W, int C, 
                           cudaStream_t s) {
   if (C % 8) throw std::runtime_error("[b200] adaptive_avgpool: C%8 != 0");
   const long long total = static_cast<long long>(N) * H * W * (C / 8);
-  adaptive_avgpool_bwd_kernel<<<min(ceil_div_ll(total, 256), 148 * 16), 256, 0, s>>>(dy, dx, N, H, W, C, OH, OW);
+  adaptive_avgpool_bwd_kernel<<<min(ceil_div_ll(total, 256), sm_count() * 16), 256, 0, s>>>(dy, dx, N, H, W, C, OH, OW);
   count_launch();
   check_last("adaptive_avgpool_bwd");
 }
@@ -348,7 +348,7 @@ void bias_grad(const bf16* dz, float* db, long long rows, int C, float scale, cu
   if (RL < 1) RL = 1;
   const int threads = CG * RL;
   long long nblk = (rows + RL * 16 - 1) / (RL * 16);
-  const long long cap = 148LL * 8 / ((c8 + CG - 1) / CG);
+  const long long cap = static_cast<long long>(sm_count()) * 8 / ((c8 + CG - 1) / CG);
   if (nblk > cap) nblk = cap;
   if (nblk < 1) nblk = 1;
   const long long rpb = (rows + nblk - 1) / nblk;
@@ -404,7 +404,7 @@ void fc_bias_act(float* acc, const float* bias, bf16* y, float* y_f32, int B, in
                  float drop_p, unsigned long long seed, unsigned long long offset, bool clear,
                  cudaStream_t s) {
   const long long quads = (static_cast<long long>(B) * N + 3) / 4;
-  fc_bias_act_kernel<<<min(ceil_div_ll(quads, 256), 148 * 8), 256, 0, s>>>(
+  fc_bias_act_kernel<<<min(ceil_div_ll(quads, 256), sm_count() * 8), 256, 0, s>>>(
       acc, bias, y, y_f32, B, N, N, relu ? 1 : 0, drop_p, seed, offset, clear ? 1 : 0);
   count_launch();
   check_last("fc_bias_act");
@@ -447,7 +447,7 @@ void fc_grad_act(float* acc, const bf16* act, bf16* dz, int B, int N, bool relu,
   if ((reinterpret_cast<uintptr_t>(acc) & 15) || (reinterpret_cast<uintptr_t>(dz) & 7) ||
       (act && (reinterpret_cast<uintptr_t>(act) & 7)))
     throw std::runtime_error("[b200] fc_grad_act: buffers must be 16-byte (fp32) / 8-byte (bf16) aligned");
-  fc_grad_act_kernel<<<min(ceil_div_ll(total / 4 + 1, 256), 148 * 8), 256, 0, s>>>(acc, act, dz, total,
+  fc_grad_act_kernel<<<min(ceil_div_ll(total / 4 + 1, 256), sm_count() * 8), 256, 0, s>>>(acc, act, dz, total,
                                                                                    relu ? 1 : 0, scale, clear ? 1 : 0);
   count_launch();
   check_last("fc_grad_act");
@@ -469,12 +469,12 @@ __global__ void cast_bf16_to_f32_kernel(const bf16* __restrict__ x, float* __res
     y[i] = __bfloat162float(x[i]);
 }
 void cast_f32_to_bf16(const float* x, bf16* y, long long n, cudaStream_t s) {
-  cast_f32_to_bf16_kernel<<<min(ceil_div_ll(n / 4 + 1, 256), 148 * 8), 256, 0, s>>>(x, y, n);
+  cast_f32_to_bf16_kernel<<<min(ceil_div_ll(n / 4 + 1, 256), sm_count() * 8), 256, 0, s>>>(x, y, n);
   count_launch();
   check_last("cast_f32_to_bf16");
 }
 void cast_bf16_to_f32(const bf16* x, float* y, long long n, cudaStream_t s) {
-  cast_bf16_to_f32_kernel<<<min(ceil_div_ll(n, 256), 148 * 8), 256, 0, s>>>(x, y, n);
+  cast_bf16_to_f32_kernel<<<min(ceil_div_ll(n, 256), sm_count() * 8), 256, 0, s>>>(x, y, n);
   count_launch();
   check_last("cast_bf16_to_f32");
 }

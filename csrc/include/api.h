@@ -13,6 +13,8 @@ typedef __nv_bfloat16 bf16;
 long long launch_count();
 void count_launch(int n = 1);
 void check_last(const char* what);
+// multiProcessorCount of the current device (cached; grids are sized from it, never from a literal)
+int sm_count();
 
 // ---- tcgen05 GEMM family (umma_launch.cu) -----------------------------------------------------
 // D[M,N] = alpha * sum_k A[m,k] * B[n,k].  a_mn: A is stored [K][M] (row stride lda) instead of

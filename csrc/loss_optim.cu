@@ -100,23 +100,31 @@ void cross_entropy_fused(const float* logits, const long long* target, bf16* dlo
 // One pass over the flat arena: read grad (fp32 local or bf16 reduced wire), update fp32 master
 // weight and both moments, emit the bf16 shadow used by the GEMMs, and zero the fp32 gradient so
 // the red.add wgrad epilogues of the next step start from zero.
-__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+// Footprint (same reasoning as allreduce.cu): the update runs on the comm stream UNDER the persistent
+// conv kernels of backward.  256 threads x <= 40 registers and no shared memory co-reside with any of
+// them, and the grid is one CTA per SM -- a background stream of HBM traffic.  (Round 1 launched 8
+// CTAs per SM: at every conv-kernel boundary the high-priority stream filled the SMs with optimizer
+// CTAs and the next conv kernel's persistent CTAs started late; bench/step_timeline.py.)
+__global__ void __launch_bounds__(256, 6) adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                             const float* __restrict__ g32, const bf16* __restrict__ g16,
                             bf16* __restrict__ shadow, long long n4, float lr, float b1, float b2,
                             float eps, float wd, float bc1_inv, float bc2_inv_sqrt, float gscale,
                             float* __restrict__ gzero) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float4 pv = reinterpret_cast<float4*>(p)[i];
-    float4 mv = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
+    // Every stream here is touched exactly once per step: cache-streaming (evict-first) loads and
+    // stores, so that ~4 GB of optimizer traffic does not flush the conv kernels' L2-resident operand
+    // tiles while it runs under backward (bench/step_timeline.py: +30 % on the 512-channel layers).
+    float4 pv = __ldcs(reinterpret_cast<const float4*>(p) + i);
+    float4 mv = __ldcs(reinterpret_cast<const float4*>(m) + i);
+    float4 vv = __ldcs(reinterpret_cast<const float4*>(v) + i);
     float g[4];
     if (g16) {
-      const uint2 raw = *reinterpret_cast<const uint2*>(g16 + i * 4);
+      const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(g16 + i * 4));
       const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
       g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
     } else {
-      const float4 gv = reinterpret_cast<const float4*>(g32)[i];
+      const float4 gv = __ldcs(reinterpret_cast<const float4*>(g32) + i);
       g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
     }
     float pp[4] = {pv.x, pv.y, pv.z, pv.w};
@@ -130,12 +138,12 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float*
       const float denom = sqrtf(vs[k]) * bc2_inv_sqrt + eps;
       pp[k] -= lr * bc1_inv * mm[k] / denom;
     }
-    reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
-    reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
-    reinterpret_cast<float4*>(v)[i] = make_float4(vs[0], vs[1], vs[2], vs[3]);
+    __stcs(reinterpret_cast<float4*>(p) + i, make_float4(pp[0], pp[1], pp[2], pp[3]));
+    __stcs(reinterpret_cast<float4*>(m) + i, make_float4(mm[0], mm[1], mm[2], mm[3]));
+    __stcs(reinterpret_cast<float4*>(v) + i, make_float4(vs[0], vs[1], vs[2], vs[3]));
     if (shadow)
-      *reinterpret_cast<uint2*>(shadow + i * 4) = make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
-    if (gzero) reinterpret_cast<float4*>(gzero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __stcs(reinterpret_cast<uint2*>(shadow + i * 4), make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3])));
+    if (gzero) __stcs(reinterpret_cast<float4*>(gzero) + i, make_float4(0.f, 0.f, 0.f, 0.f));
   }
 }
 
@@ -146,15 +154,13 @@ void adam_fused(float* p, float* m, float* v, const float* g32, const bf16* g16,
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
   const long long n4 = n / 4;
-  // The update runs on the side stream under the persistent conv kernels: how many of its CTAs sit
-  // on an SM decides how much register space a late-starting conv CTA finds.
-  // Tunable without a rebuild: B200_ADAM_CTAS_PER_SM (default 8).
+  // Tunable without a rebuild: B200_ADAM_CTAS_PER_SM (default 4).
   static const int per_sm = [] {
     const char* e = getenv("B200_ADAM_CTAS_PER_SM");
-    const int v = e ? atoi(e) : 8;
-    return v >= 1 && v <= 16 ? v : 8;
+    const int v = e ? atoi(e) : 4;
+    return v >= 1 && v <= 16 ? v : 4;
   }();
-  const long long cap = 148LL * per_sm;
+  const long long cap = static_cast<long long>(sm_count()) * per_sm;
   const int blocks = static_cast<int>(n4 / 256 + 1 < cap ? n4 / 256 + 1 : cap);
   adam_kernel<<<blocks, 256, 0, s>>>(p, m, v, g32, g16, shadow, n4, lr, beta1, beta2, eps, weight_decay,
                                      static_cast<float>(1.0 / bc1), static_cast<float>(1.0 / sqrt(bc2)),
@@ -165,20 +171,20 @@ void adam_fused(float* p, float* m, float* v, const float* g32, const bf16* g16,
 
 // --------------------------------------------------------------------------------------- SGD
 // torch.optim.SGD(momentum) semantics: buf = g (first step) | momentum*buf + g ; p -= lr*buf.
-__global__ void sgd_kernel(float* __restrict__ p, float* __restrict__ mom, const float* __restrict__ g32,
+__global__ void __launch_bounds__(256, 6) sgd_kernel(float* __restrict__ p, float* __restrict__ mom, const float* __restrict__ g32,
                            const bf16* __restrict__ g16, bf16* __restrict__ shadow, long long n4, float lr,
                            float momentum, float wd, int first, float gscale, float* __restrict__ gzero) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float4 pv = reinterpret_cast<float4*>(p)[i];
-    float4 bv = reinterpret_cast<float4*>(mom)[i];
+    float4 pv = __ldcs(reinterpret_cast<const float4*>(p) + i);       // streaming, see adam_kernel
+    float4 bv = __ldcs(reinterpret_cast<const float4*>(mom) + i);
     float g[4];
     if (g16) {
-      const uint2 raw = *reinterpret_cast<const uint2*>(g16 + i * 4);
+      const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(g16 + i * 4));
       const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
       g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
     } else {
-      const float4 gv = reinterpret_cast<const float4*>(g32)[i];
+      const float4 gv = __ldcs(reinterpret_cast<const float4*>(g32) + i);
       g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
     }
     float pp[4] = {pv.x, pv.y, pv.z, pv.w};
@@ -189,11 +195,11 @@ __global__ void sgd_kernel(float* __restrict__ p, float* __restrict__ mom, const
       bb[k] = first ? gk : momentum * bb[k] + gk;
       pp[k] -= lr * bb[k];
     }
-    reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
-    reinterpret_cast<float4*>(mom)[i] = make_float4(bb[0], bb[1], bb[2], bb[3]);
+    __stcs(reinterpret_cast<float4*>(p) + i, make_float4(pp[0], pp[1], pp[2], pp[3]));
+    __stcs(reinterpret_cast<float4*>(mom) + i, make_float4(bb[0], bb[1], bb[2], bb[3]));
     if (shadow)
-      *reinterpret_cast<uint2*>(shadow + i * 4) = make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
-    if (gzero) reinterpret_cast<float4*>(gzero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __stcs(reinterpret_cast<uint2*>(shadow + i * 4), make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3])));
+    if (gzero) __stcs(reinterpret_cast<float4*>(gzero) + i, make_float4(0.f, 0.f, 0.f, 0.f));
   }
 }
 
@@ -202,7 +208,8 @@ void sgd_fused(float* p, float* mom, const float* g32, const bf16* g16, bf16* sh
                float* g32_to_zero, cudaStream_t s) {
   if (n % 4) throw std::runtime_error("[b200] sgd_fused: n must be a multiple of 4");
   const long long n4 = n / 4;
-  const int blocks = static_cast<int>(n4 / 256 + 1 < 148 * 8 ? n4 / 256 + 1 : 148 * 8);
+  const long long cap = sm_count();
+  const int blocks = static_cast<int>(n4 / 256 + 1 < cap ? n4 / 256 + 1 : cap);
   sgd_kernel<<<blocks, 256, 0, s>>>(p, mom, g32, g16, shadow, n4, lr, momentum, weight_decay,
                                     first_step ? 1 : 0, grad_scale, g32_to_zero);
   count_launch();

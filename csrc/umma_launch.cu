@@ -79,16 +79,17 @@ static void map_nhwc(CUtensorMap* m, const bf16* p, int N, int H, int W, int C, 
   encode(m, p, 4, dims, str, box);
 }
 
-static int num_sms() {
+int sm_count() {
   static int n = 0;
   if (!n) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    if (n <= 0) throw std::runtime_error("[b200] cannot query the SM count of the current device");
   }
   return n;
 }
+static int num_sms() { return sm_count(); }
 
 // EXPERIMENTAL (B200_DYNAMIC_TILES=1, not yet run on hardware): dynamic tile scheduler, see
 // umma_core_dyn.cuh.  64 device counters used round-robin; a counter is never reset -- the host

@@ -110,6 +110,7 @@ class NativeEngine:
         self.class_weights: Optional[torch.Tensor] = None
         self.timer = PhaseTimer(profile == "events", nvtx=(profile == "nvtx"))
         self._comm_events: Optional[list] = None     # [(start, end, wire bytes)] while comm timing is on
+        self._tl: Optional[list] = None              # step timeline marks (timeline())
         self.nvtx = profile == "nvtx"
         self.world = dist.get_world_size() if (distributed and distributed_is_initialized()) else 1
         self.rank = dist.get_rank() if (distributed and distributed_is_initialized()) else 0
@@ -191,6 +192,9 @@ class NativeEngine:
         if zero1 and not self.zero1 and self.world > 1:
             raise ValueError("--zero1 needs Adam, the bf16 wire and all ranks in one NVLink domain")
         self._zero1_buckets: set = set()
+        # the fused ZeRO-1 kernel keeps less in flight per CTA (128 threads, one switch reduction +
+        # 96 bytes of optimizer state each): more, equally thin, CTAs
+        self.zero1_ctas = int(os.environ.get("B200_ZERO1_CTAS", "128"))
 
         self._build_buffers()
 
@@ -219,7 +223,7 @@ class NativeEngine:
             for bi in sorted(self._zero1_buckets):
                 bk = self.plan.buckets[bi]
                 tmp = torch.zeros(bk.end - bk.start, dtype=F32, device=self.device)
-                for a, b in self.arena.owned_ranges(bk.start, bk.end - bk.start, self.comm_ctas):
+                for a, b in self.arena.owned_ranges(bk.start, bk.end - bk.start, self.zero1_ctas):
                     tmp[a - bk.start:b - bk.start] = arena[a:b]
                 dist.all_reduce(tmp)
                 arena[bk.start:bk.end] = tmp
@@ -399,12 +403,14 @@ class NativeEngine:
             if self.pool_masks[i] is not None:           # experimental fused conv + ReLU + pool
                 x, _ = ops.conv3x3_fprop_pool(x, self._w(c.name), self._b(c.name), out=self.pools[i][:b],
                                               mask=self.pool_masks[i][:b])
+                self._mark("fwd " + c.name)
                 continue
             y = self.acts[i][:b]
             C.conv_fprop(x, self._w(c.name), self._b(c.name), y, True, 0)
             x = y
             if c.pool_after:
                 x = ops.maxpool2x2(y, out=self.pools[i][:b])
+            self._mark("fwd " + c.name)
         if self.avg is not None:
             x = ops.adaptive_avgpool(x, spec.pooled_hw, spec.pooled_hw, out=self.avg[:b])
         self.feat = x
@@ -465,6 +471,7 @@ class NativeEngine:
                                 relu=prev.relu, drop_p=prev.dropout if self.train_dropout else 0.0)
             else:
                 ops.fc_grad_act(dacc, None, self.dfeat[:b].view(b, -1), B=b, N=f.fin, relu=False)
+            self._mark("bwd " + f.name)
         # ---- feature map gradient ------------------------------------------------------------
         g = self.dfeat[:b]
         if self.avg is not None:
@@ -502,6 +509,7 @@ class NativeEngine:
                     ops.gemm(dz.view(M, c.cout), self.col0[:M], self._grad(c.name + ".weight"), M=c.cout,
                              N=L.CONV0_K, K=M, a_mn=True, b_mn=True, epi="f32_atomic", ksplit=ks, ldo=L.CONV0_K)
                 self._bucket_done(c.name + ".weight")
+                self._mark("bwd " + c.name)
                 break
             prev = convs[i - 1]
             x_in = self.pools[i - 1][:b] if prev.pool_after else self.acts[i - 1][:b]
@@ -514,6 +522,7 @@ class NativeEngine:
                          self._grad(prev.name + ".bias") if fuse else None, 0)
             bias_fused = fuse
             self._bucket_done(c.name + ".weight")      # after dgrad: it reads the pre-update weights
+            self._mark("bwd " + c.name)
             pp ^= 1
             g = dx
 
@@ -554,7 +563,9 @@ class NativeEngine:
                 ev.record()
                 self.comm_stream.wait_event(ev)
                 with torch.cuda.stream(self.comm_stream):
+                    self._mark("opt%d start" % bi, "comm")
                     self._apply_update(s, e, None, zero=not self._bucket_store_only[bi])
+                    self._mark("opt%d end" % bi, "comm")
             return
         ev = torch.cuda.Event()
         ev.record()
@@ -575,14 +586,17 @@ class NativeEngine:
             # stay replicated -- biases are read from the fp32 master, which under ZeRO-1 is current on
             # the owner rank only.
             if self.zero1 and self.apply_updates and prepacked and algo != "oneshot":
+                self._mark("z1_%d start" % bi, "comm")
                 self.arena.zero1_step(None if prepacked else self.g32, self.p32, self.m32, self.v32, self.w16,
-                                      s, e - s, algo=algo, slot=bi % self.arena.slots, max_ctas=self.comm_ctas,
+                                      s, e - s, algo=algo, slot=bi % self.arena.slots, max_ctas=self.zero1_ctas,
                                       inv_world=1.0 / self.world, lr=self.lr, beta1=self.beta1, beta2=self.beta2,
                                       eps=self.eps, weight_decay=self.weight_decay, step=self.step_count)
                 self._zero1_buckets.add(bi)
+                self._mark("z1_%d end" % bi, "comm")
                 return
             to_f32 = (algo == "oneshot" or self.unpack_fp32 or self.arena.wire_dtype == F32
                       or not self.apply_updates)
+            self._mark("ar%d start" % bi, "comm")
             ev0 = None
             if self._comm_events is not None:    # observability: device time of every reduction
                 ev0 = torch.cuda.Event(enable_timing=True)
@@ -596,9 +610,11 @@ class NativeEngine:
                 self._comm_events.append((ev0, ev1, (e - s) * self.arena.wire.element_size()))
             if self.cross_group is not None:     # node sums (already x 1/world) -> job sum, over NCCL
                 dist.all_reduce(self.g32[s:e] if to_f32 else self.arena.wire[s:e], group=self.cross_group)
+            self._mark("ar%d end" % bi, "comm")
             if self.apply_updates:
                 self._apply_update(s, e, None if to_f32 else self.arena.wire[s:e],
                                    zero=not (prepacked or self._bucket_store_only[bi]))
+                self._mark("opt%d end" % bi, "comm")
 
     def _end_step(self) -> None:
         torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
@@ -617,9 +633,11 @@ class NativeEngine:
         t = self.timer
         if self.nvtx:
             torch.cuda.nvtx.range_push("step")
+        self._mark("step start")
         t.start("input")
         b = self._stage_input(batch)
         t.stop("input")
+        self._mark("input")
         t.start("forward")
         self._forward(b, train=True)
         ld = self.fc_dz[-1].shape[1]
@@ -627,11 +645,13 @@ class NativeEngine:
         ops.cross_entropy(self.logits[:b], self.labels_dev[:b], self.fc_dz[-1][:b], ld, meter, self.loss_buf,
                           class_weights=self.class_weights)
         self._release_input()
+        self._mark("loss")
         t.stop("forward")
         t.start("backward+reduce+update")
         self._begin_step()
         self._backward(b)
         self._end_step()
+        self._mark("step end (joined comm)")
         t.stop("backward+reduce+update")
         if self.nvtx:
             torch.cuda.nvtx.range_pop()
@@ -653,6 +673,30 @@ class NativeEngine:
 
     def sync(self) -> None:
         torch.cuda.synchronize(self.device)
+
+    # ---- step timeline (SURVEY 5.1 tracing; there is no nsys on the box) ----------------------------
+    def timeline(self, on: bool) -> None:
+        """Record a CUDA event after every layer's kernels on the compute stream and around every
+        all-reduce / optimizer launch on the comm stream.  ``timeline_report()`` turns them into
+        milliseconds since the start of the step: which bucket's reduction ran under which layer's
+        backward, and what (if anything) is exposed after the last wgrad."""
+        self._tl = [] if on else None
+
+    def _mark(self, name: str, lane: str = "compute") -> None:
+        if self._tl is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()                      # on the current stream
+            self._tl.append((name, lane, ev))
+
+    def timeline_report(self) -> list:
+        """[(name, lane, ms since the step's first mark)] for everything recorded since timeline(True)."""
+        if not self._tl:
+            return []
+        self.sync()
+        t0 = self._tl[0][2]
+        out = [(n, lane, round(t0.elapsed_time(ev), 4)) for n, lane, ev in self._tl]
+        self._tl = []
+        return out
 
     # ---- gradient all-reduce observability (SURVEY 5.5: GB/s and roofline fraction) -----------------
     def comm_timing(self, on: bool) -> None:

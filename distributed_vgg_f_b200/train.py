@@ -48,11 +48,22 @@ def manage_training(args) -> Trainer:
         init_distributed(args.init_url, args.rank, args.world_size, device,
                          getattr(args, "backend", None))
 
-    if getattr(args, "synthetic", 0) and not os.path.isdir(os.path.join(args.root_dir, "TrainData")):
-        if args.rank == 0:
+    if getattr(args, "synthetic", 0):
+        # Rank 0 alone decides whether the set has to be generated, writes it into a temporary
+        # directory and renames it into place; EVERY rank then passes the same barrier.  (A per-rank
+        # isdir() test races with rank 0 creating the directory: a late rank would skip the barrier,
+        # scan a half-written folder and pair rank 0's barrier with some other collective.)
+        if args.rank == 0 and not os.path.isdir(os.path.join(args.root_dir, "TrainData")):
+            import shutil
+
             from .data.synthetic import make_synthetic_imagefolder
-            make_synthetic_imagefolder(args.root_dir, train_per_class=args.synthetic,
+            tmp = args.root_dir.rstrip("/") + ".tmp%d" % os.getpid()
+            make_synthetic_imagefolder(tmp, train_per_class=args.synthetic,
                                        val_per_class=max(args.synthetic // 4, 1), seed=args.seed)
+            os.makedirs(args.root_dir, exist_ok=True)
+            for sub in sorted(os.listdir(tmp), reverse=True):     # TrainData last
+                os.replace(os.path.join(tmp, sub), os.path.join(args.root_dir, sub))
+            shutil.rmtree(tmp, ignore_errors=True)
         if distributed_is_initialized():
             torch.distributed.barrier()
 
@@ -96,6 +107,14 @@ def manage_training(args) -> Trainer:
         print("[Info] resumed from {} at epoch {}".format(args.resume, start_epoch))
 
     base_lr = args.learning_rate
+    if args.resume and args.lr_step and start_epoch > 1:
+        # a run resumed behind an LR-step boundary continues at the decayed rate on BOTH back ends
+        resumed_lr = base_lr * (args.lr_gamma ** ((start_epoch - 1) // args.lr_step))
+        if optimizer is not None:
+            for g in optimizer.param_groups:
+                g["lr"] = resumed_lr
+        else:
+            model.set_lr(resumed_lr)
 
     def on_epoch_end(epoch: int, trainer: Trainer) -> None:
         if args.lr_step and epoch % args.lr_step == 0:
@@ -108,6 +127,10 @@ def manage_training(args) -> Trainer:
         if args.save:
             ckpt.save_checkpoint(args.save, model, optimizer, epoch, vars(args),
                                  is_rank0=(args.rank == 0))
+            # rank 0 is busy with a ~1.6 GB D2H copy + torch.save: hold the other ranks HERE, on the
+            # host, instead of letting them spin inside the next epoch's first all-reduce kernel
+            if distributed_is_initialized():
+                torch.distributed.barrier()
         if args.log_jsonl and args.rank == 0:
             rec = dict(trainer.history[-1], time=time.time(), world_size=args.world_size)
             if hasattr(model, "phase_times"):
