@@ -152,7 +152,7 @@ def run_native(args):
     eng = NativeEngine(spec, device=device, batch=args.batch, lr=1e-5, optimizer=args.optimizer,
                        allreduce=args.allreduce, wire_dtype=args.wire_dtype, bucket_mb=args.bucket_mb,
                        seed=0, input_hw=args.hw, comm_ctas=args.comm_ctas,
-                       zero1=args.zero1 and world > 1)
+                       zero1={"auto": "auto", "on": True, "off": False}[args.zero1] if world > 1 else False)
     host = make_host_batches(torch, 4, args.batch, args.num_classes, seed=rank + 1)
     dev_batches = [FusedBatch(b.images_u8.to(device), b.params.to(device), b.labels.to(device), b.resized_hw, None)
                    for b in host]
@@ -250,9 +250,14 @@ def run_native(args):
 
 
 # ------------------------------------------------------------------------------ reference arm
-def run_reference(args):
+def run_reference(args, bf16: bool = False):
     """Unmodified reference (baseline/_ref/distributedVggf.py): its model factory, its Trainer loop,
-    its DataManager; torch DDP over NCCL as in SURVEY D4 (BACKEND constant -> "nccl")."""
+    its DataManager; torch DDP over NCCL as in SURVEY D4 (BACKEND constant -> "nccl").
+
+    ``bf16=True`` (--impl reference-bf16) is a CONTEXT arm, not the reference arm: the same model
+    object and loop under ``torch.autocast(bfloat16)`` with channels_last tensors and DDP's
+    ``bf16_compress_hook`` -- the best the library stack (cuDNN / cuBLAS / NCCL) does for this model at
+    the precision the native engine computes in (SURVEY 5.8 "baseline to beat")."""
     ref_dir = os.path.join(ROOT, "baseline", "_ref")
     if not os.path.exists(os.path.join(ref_dir, "distributedVggf.py")):
         print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref missing: run python baseline/install_ref.py"}))
@@ -281,10 +286,21 @@ def run_reference(args):
     if world > 1:
         dist.init_process_group(backend=dstUt.BACKEND, device_id=device)
     torch.manual_seed(0)
-    model = ref.vgg_funnel_model(args.num_classes)
+    if args.model == "vgg16":
+        # BASELINE config #3 (VGG-16 / 1000 classes): the reference has no such factory -- its model IS
+        # torchvision's VGG-16 with the last layer swapped (distributedVggf.py:46-57), so the arm is
+        # torchvision's VGG-16 as is, driven by the reference's Trainer loop
+        model = _orig_vgg16(weights=None, num_classes=args.num_classes)
+    else:
+        model = ref.vgg_funnel_model(args.num_classes)
+    if bf16:
+        model = model.to(memory_format=torch.channels_last)
     if ref.distributed_is_initialized():
         model.to(device)
         model = nn.parallel.DistributedDataParallel(model)     # distributedVggf.py:224-225
+        if bf16:
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            model.register_comm_hook(None, default_hooks.bf16_compress_hook)
     else:
         model = nn.DataParallel(model, device_ids=[local])     # distributedVggf.py:227 (1 visible GPU/process)
         model.to(device)
@@ -294,6 +310,10 @@ def run_reference(args):
     g = torch.Generator().manual_seed(rank)
     dev_batches = [(torch.randn(B, 3, args.hw, args.hw, generator=g).to(device),
                     torch.randint(0, args.num_classes, (B,), generator=g).to(device)) for _ in range(4)]
+    if bf16:
+        dev_batches = [(x.contiguous(memory_format=torch.channels_last), y) for x, y in dev_batches]
+    import contextlib
+    amp = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if bf16 else contextlib.nullcontext
 
     class Loader:
         def __init__(self, n):
@@ -304,13 +324,18 @@ def run_reference(args):
                 yield dev_batches[k % len(dev_batches)]
 
     trainer = ref.Trainer(model, optimizer, Loader(args.warmup), Loader(0), device)
-    trainer._Trainer__train()                    # warm-up through the reference's own loop
+    with amp():
+        trainer._Trainer__train()                # warm-up through the reference's own loop
     torch.cuda.synchronize(device)
     clocks = ClockSampler(local)
     clocks.start()
     trainer.train_loader = Loader(args.steps)
-    ms, _ = timed_region(torch, dist, world, device, lambda k: trainer._Trainer__train() if k == 0 else None,
-                         args.steps)
+    def whole_loop(k):
+        if k == 0:
+            with amp():
+                trainer._Trainer__train()
+
+    ms, _ = timed_region(torch, dist, world, device, whole_loop, args.steps)
 
     # end-to-end: the reference's DataManager (PIL + transforms, num_workers=0) on a synthetic ImageFolder
     e2e = None
@@ -323,8 +348,7 @@ def run_reference(args):
         dm = ref.DataManager(root_folder=root, mini_batch=B, train=True)
         n_steps = len(dm.get_loader())
         trainer.train_loader = dm.get_loader()
-        ms_e, wall_e = timed_region(torch, dist, world, device,
-                                    lambda k: trainer._Trainer__train() if k == 0 else None, 1)
+        ms_e, wall_e = timed_region(torch, dist, world, device, whole_loop, 1)
         e2e = {"value": round(B * world * n_steps / (max(ms_e, wall_e) / 1e3), 2), "unit": "images/sec",
                "steps": n_steps, "h2d_bytes_per_step": B * 3 * args.hw * args.hw * 4 + B * 8,
                "d2h_bytes_per_step": 8,
@@ -340,9 +364,11 @@ def run_reference(args):
             "value": round(value, 2), "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": round(value / BASELINE_IMG_S[world], 2) if world in BASELINE_IMG_S else None,
-            "dtype": "fp32 (reference default: TF32 conv via cuDNN, fp32 matmul)", "impl": "reference",
+            "dtype": ("bf16 autocast + channels_last + bf16_compress_hook (context arm)" if bf16
+                      else "fp32 (reference default: TF32 conv via cuDNN, fp32 matmul)"),
+            "impl": "reference-bf16" if bf16 else "reference",
             "data": "synthetic: random fp32 224x224 device tensors (value) / synthetic 128x128 ImageFolder (e2e)",
-            "config": {"model": "vggf", "num_classes": args.num_classes, "global_batch": gb, "per_gpu_batch": B,
+            "config": {"model": args.model, "num_classes": args.num_classes, "global_batch": gb, "per_gpu_batch": B,
                        "input": "%dx%d" % (args.hw, args.hw), "parallelism": "dp%d" % world,
                        "backend": "nccl DDP (reference BACKEND constant set to nccl)", "optimizer": "adam"},
             "e2e": e2e, "gpu_launches": 0, "clocks": clk}), flush=True)
@@ -355,7 +381,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "reference-bf16"])
     ap.add_argument("--model", default="vggf")
     ap.add_argument("--num-classes", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64)
@@ -366,7 +392,8 @@ def main():
     ap.add_argument("--bucket-mb", type=float, default=32.0)
     ap.add_argument("--comm-ctas", type=int, default=48)
     ap.add_argument("--e2e-steps", type=int, default=4)
-    ap.add_argument("--zero1", action="store_true", help="experimental fused ZeRO-1 step (docs/EXPERIMENTAL.md)")
+    ap.add_argument("--zero1", default="auto", choices=["auto", "on", "off"],
+                    help="fused reduce-scatter + Adam + all-gather for the FC-weight buckets (auto: from 4 ranks up)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -377,8 +404,8 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
                os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    if args.impl == "reference":
-        run_reference(args)
+    if args.impl in ("reference", "reference-bf16"):
+        run_reference(args, bf16=args.impl == "reference-bf16")
     else:
         run_native(args)
 

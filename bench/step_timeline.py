@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--model", default="vggf")
     ap.add_argument("--num-classes", type=int, default=3)
     ap.add_argument("--tag", default="")
-    ap.add_argument("--zero1", action="store_true")
+    ap.add_argument("--zero1", default="auto", choices=["auto", "on", "off"])
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
@@ -42,7 +42,7 @@ def main():
     from distributed_vgg_f_b200.models.vggf import get_spec
 
     eng = NativeEngine(get_spec(a.model, a.num_classes), device=dev, batch=a.batch, lr=1e-5, seed=0,
-                       comm_ctas=a.comm_ctas, zero1=a.zero1 and world > 1)
+                       comm_ctas=a.comm_ctas, zero1={"auto": "auto", "on": True, "off": False}[a.zero1] if world > 1 else False)
     host = make_host_batches(torch, 4, a.batch, a.num_classes, seed=rank + 1, pin=False)
     batches = [FusedBatch(b.images_u8.to(dev), b.params.to(dev), b.labels.to(dev), b.resized_hw, None) for b in host]
     for k in range(a.warmup):
@@ -70,15 +70,15 @@ def main():
         json.dump({"world": world, "comm_ctas": a.comm_ctas, "rows": rows, "step_end_max_over_ranks_ms": float(t_end)},
                   open(out, "w"), indent=1)
         comp = [r for r in rows if r["lane"] == "compute"]
-        comm = [r for r in rows if r["lane"] == "comm"]
+        comm = [r for r in rows if r["lane"] != "compute"]
         print("compute stream (ms since step start; delta):")
         prev = 0.0
         for r in comp:
             print("  %-28s %8.3f  +%.3f" % (r["name"], r["ms"], r["ms"] - prev))
             prev = r["ms"]
-        print("comm stream:")
+        print("side streams (comm = reductions, opt = optimizer):")
         for r in comm:
-            print("  %-28s %8.3f" % (r["name"], r["ms"]))
+            print("  %-5s %-28s %8.3f" % (r["lane"], r["name"], r["ms"]))
         last_w = max(r["ms"] for r in comp if r["name"].startswith("bwd "))
         print("last wgrad enqueued-done at %.3f ms, step end (joined comm) at %.3f ms -> exposed tail %.3f ms"
               % (last_w, comp[-1]["ms"], comp[-1]["ms"] - last_w))

@@ -308,6 +308,16 @@ void allreduce_fused(const CommCtx& ctx, const float* grad_f32, float* grad_out_
   a.c = ctx; a.grad = grad_f32; a.grad_out = grad_out_f32; a.start = start; a.n = n;
   a.inv_world = inv_world; a.slot = slot; a.epoch = epoch;
   const int G = allreduce_grid(n, ctx.world, max_ctas, wire_fp32);
+  static const bool carve = [] {
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(allreduce_kernel<AR_ONESHOT, false>));
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(allreduce_kernel<AR_ONESHOT, true>));
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(allreduce_kernel<AR_TWOSHOT, false>));
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(allreduce_kernel<AR_TWOSHOT, true>));
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(allreduce_kernel<AR_NVLS, false>));
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(allreduce_kernel<AR_NVLS, true>));
+    return true;
+  }();
+  (void)carve;
 #define AR_LAUNCH(ALGO)                                                           \
   if (wire_fp32) allreduce_kernel<ALGO, true><<<G, AR_THREADS, 0, s>>>(a);        \
   else allreduce_kernel<ALGO, false><<<G, AR_THREADS, 0, s>>>(a);
@@ -472,6 +482,12 @@ void zero1_step(const CommCtx& ctx, float* grad_f32, float* p, float* m, float* 
   a.bc1_inv = static_cast<float>(1.0 / (1.0 - pow(static_cast<double>(beta1), step)));
   a.bc2_inv_sqrt = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(beta2), step)));
   const int G = allreduce_grid(n, ctx.world, max_ctas, false);
+  static const bool carve = [] {
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(zero1_kernel<AR_NVLS>));
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(zero1_kernel<AR_TWOSHOT>));
+    return true;
+  }();
+  (void)carve;
   if (algo == AR_NVLS) zero1_kernel<AR_NVLS><<<G, Z1_THREADS, 0, s>>>(a);
   else zero1_kernel<AR_TWOSHOT><<<G, Z1_THREADS, 0, s>>>(a);
   count_launch();

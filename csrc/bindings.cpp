@@ -379,6 +379,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("release", &PyPrefetcher::release)
       .def("stop", &PyPrefetcher::stop);
   py::class_<PyComm>(m, "Comm");
+  m.def("probe_background", [](at::Tensor buf, int64_t mode, int64_t ctas, int64_t reps, at::Tensor sink) {
+    b200::probe_background(f32p(buf), buf.numel(), (int)mode, (int)ctas, (int)reps, f32p(sink), cur_stream());
+  });
   m.def("make_comm", &make_comm);
   m.def("allreduce", &allreduce);
   m.def("zero1_step", &zero1_step);

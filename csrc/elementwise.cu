@@ -479,4 +479,50 @@ void cast_bf16_to_f32(const bf16* x, float* y, long long n, cudaStream_t s) {
   check_last("cast_bf16_to_f32");
 }
 
+// ------------------------------------------------------------------------ co-residency probe
+// bench/interference.py: a thin (256 threads, <= 40 registers, no shared memory) background kernel that
+// exercises ONE resource, to find out what a comm-stream CTA sharing an SM with a persistent tcgen05
+// conv CTA takes away from it.  mode 0: dependent FMA chain (issue slots only), 1: streaming 16-byte
+// loads, 2: streaming 16-byte stores, 3: load + store, 4: sqrt / divide chain (MUFU),
+// 5: sleep (resident warps that issue almost nothing).
+__global__ void __launch_bounds__(256, 6)
+probe_background_kernel(float4* __restrict__ buf, long long n4, int mode, int reps, float* __restrict__ sink) {
+  float acc = threadIdx.x * 1e-6f;
+  for (int r = 0; r < reps; ++r) {
+    if (mode == 0) {
+      for (int k = 0; k < 4096; ++k) acc = fmaf(acc, 1.000001f, 1e-7f);
+    } else if (mode == 4) {
+      for (int k = 0; k < 1024; ++k) acc = sqrtf(acc + 1.5f) / (acc + 2.5f);
+    } else if (mode == 5) {
+      for (int k = 0; k < 64; ++k) __nanosleep(1000);
+    } else {
+      for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+           i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        if (mode == 1) {
+          const float4 v = __ldcs(buf + i);
+          acc += v.x + v.w;
+        } else if (mode == 2) {
+          __stcs(buf + i, make_float4(acc, 0.f, 0.f, 0.f));
+        } else {
+          float4 v = __ldcs(buf + i);
+          v.x += 1.f;
+          __stcs(buf + i, v);
+        }
+      }
+    }
+  }
+  if (acc == 12345.678f) *sink = acc;
+}
+void probe_background(float* buf, long long n, int mode, int ctas, int reps, float* sink, cudaStream_t s) {
+  static const bool carve = [] {
+    const char* e = getenv("B200_PROBE_CARVEOUT");
+    if (e && e[0] == '1') prefer_max_shared_carveout(reinterpret_cast<const void*>(probe_background_kernel));
+    return true;
+  }();
+  (void)carve;
+  probe_background_kernel<<<ctas, 256, 0, s>>>(reinterpret_cast<float4*>(buf), n / 4, mode, reps, sink);
+  count_launch();
+  check_last("probe_background");
+}
+
 }  // namespace b200

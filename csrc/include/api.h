@@ -15,6 +15,13 @@ void count_launch(int n = 1);
 void check_last(const char* what);
 // multiProcessorCount of the current device (cached; grids are sized from it, never from a literal)
 int sm_count();
+// Kernels that run on the comm stream UNDER the persistent conv kernels must ask for the same L1 /
+// shared-memory split as those (maximum shared memory): an SM only changes its carve-out when it is
+// empty, so a resident CTA of a kernel with the default (L1-heavy) preference keeps every conv CTA --
+// which needs > 200 KB of shared memory -- off that SM until it exits (bench/interference.py: a
+// background kernel that only sleeps slowed the convolutions by 1.3-1.6x).  Call once per kernel.
+void prefer_max_shared_carveout(const void* kernel);
+bool comm_carveout_enabled();   // B200_COMM_CARVEOUT=0 switches the above off (A/B measurements)
 
 // ---- tcgen05 GEMM family (umma_launch.cu) -----------------------------------------------------
 // D[M,N] = alpha * sum_k A[m,k] * B[n,k].  a_mn: A is stored [K][M] (row stride lda) instead of
@@ -77,6 +84,8 @@ void fc_bias_act(float* acc, const float* bias, bf16* y, float* y_f32, int B, in
 // FC backward epilogue: dz = acc * (act > 0) * dropmask/(1-p) -> bf16; acc cleared.
 void fc_grad_act(float* acc, const bf16* act, bf16* dz, int B, int N, bool relu, float drop_p,
                  unsigned long long seed, unsigned long long offset, bool clear, cudaStream_t s);
+// co-residency probe (bench/interference.py): thin background kernel exercising one SM resource
+void probe_background(float* buf, long long n, int mode, int ctas, int reps, float* sink, cudaStream_t s);
 void cast_f32_to_bf16(const float* x, bf16* y, long long n, cudaStream_t s);
 void cast_bf16_to_f32(const bf16* x, float* y, long long n, cudaStream_t s);
 

@@ -160,6 +160,8 @@ void adam_fused(float* p, float* m, float* v, const float* g32, const bf16* g16,
     const int v = e ? atoi(e) : 4;
     return v >= 1 && v <= 16 ? v : 4;
   }();
+  static const bool carve = (prefer_max_shared_carveout(reinterpret_cast<const void*>(adam_kernel)), true);
+  (void)carve;
   const long long cap = static_cast<long long>(sm_count()) * per_sm;
   const int blocks = static_cast<int>(n4 / 256 + 1 < cap ? n4 / 256 + 1 : cap);
   adam_kernel<<<blocks, 256, 0, s>>>(p, m, v, g32, g16, shadow, n4, lr, beta1, beta2, eps, weight_decay,
@@ -208,7 +210,9 @@ void sgd_fused(float* p, float* mom, const float* g32, const bf16* g16, bf16* sh
                float* g32_to_zero, cudaStream_t s) {
   if (n % 4) throw std::runtime_error("[b200] sgd_fused: n must be a multiple of 4");
   const long long n4 = n / 4;
-  const long long cap = sm_count();
+  static const bool carve = (prefer_max_shared_carveout(reinterpret_cast<const void*>(sgd_kernel)), true);
+  (void)carve;
+  const long long cap = static_cast<long long>(sm_count()) * 4;
   const int blocks = static_cast<int>(n4 / 256 + 1 < cap ? n4 / 256 + 1 : cap);
   sgd_kernel<<<blocks, 256, 0, s>>>(p, mom, g32, g16, shadow, n4, lr, momentum, weight_decay,
                                     first_step ? 1 : 0, grad_scale, g32_to_zero);

@@ -91,6 +91,21 @@ int sm_count() {
 }
 static int num_sms() { return sm_count(); }
 
+bool comm_carveout_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200_COMM_CARVEOUT");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+void prefer_max_shared_carveout(const void* kernel) {
+  if (!comm_carveout_enabled()) return;
+  const cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               cudaSharedmemCarveoutMaxShared);
+  if (err != cudaSuccess)
+    throw std::runtime_error(std::string("[b200] cudaFuncSetAttribute(carveout): ") + cudaGetErrorString(err));
+}
+
 // EXPERIMENTAL (B200_DYNAMIC_TILES=1, not yet run on hardware): dynamic tile scheduler, see
 // umma_core_dyn.cuh.  64 device counters used round-robin; a counter is never reset -- the host
 // tracks how far every launch advances it (num_tiles claims + one over-claim per CTA).

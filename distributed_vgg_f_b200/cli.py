@@ -99,9 +99,10 @@ def build_parser() -> argparse.ArgumentParser:
                           "hard-codes GLOO_SOCKET_IFNAME=eth0, distributedVggf.py:296; default: auto-detect)")
     ext.add_argument("--eval-only", action="store_true",
                      help="one validation pass (typically with --resume <checkpoint>) and exit")
-    ext.add_argument("--zero1", action="store_true",
-                     help="EXPERIMENTAL: shard the Adam state across the ranks of one NVLink domain -- "
-                          "reduce-scatter + optimizer + all-gather of the new bf16 weights in one kernel")
+    ext.add_argument("--zero1", default="auto", choices=["auto", "on", "off"],
+                     help="shard the Adam state of the FC weights (88 %% of the parameters) across the ranks of one "
+                          "NVLink domain: reduce-scatter + optimizer + all-gather of the new bf16 weights in ONE "
+                          "kernel per bucket (auto: from 4 ranks up)")
     ext.add_argument("--reference-order", action="store_true",
                      help="replay the reference's identical-shuffle-every-epoch behaviour")
     ext.add_argument("--shard-eval", action="store_true",

@@ -87,7 +87,7 @@ class NativeEngine:
                  bucket_mb: float = 32.0, seed: int = 0, pretrained_state: Optional[dict] = None,
                  profile: Optional[str] = None, input_hw: int = DATA.crop, comm_ctas: int = 48,
                  init_state: Optional[Dict[str, torch.Tensor]] = None, unpack_fp32: bool = False,
-                 distributed: bool = True, zero1: bool = False, conv_bucket_mb: float = 9.5,
+                 distributed: bool = True, zero1="auto", conv_bucket_mb: float = 9.5,
                  tail_bucket_kb: float = 2400.0, same_dropout_all_ranks: bool = False) -> None:
         ops.require()
         if compute_dtype != "bf16":
@@ -146,6 +146,12 @@ class NativeEngine:
         # high priority by default: a ready bucket should start reducing at once.  B200_COMM_PRIORITY=0
         # lets the comm / optimizer CTAs yield to the conv kernels instead.
         self.comm_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("B200_COMM_PRIORITY", "-1")))
+        # Second side stream for the optimizer: the reduction of bucket k+1 (NVLink-bound) runs while
+        # bucket k is being updated (HBM-bound).  On ONE stream the two add up -- at 2 ranks 24 x
+        # (all-reduce + Adam) is 5.0 ms of serial work against 4.6 ms of backward, i.e. the comm stream,
+        # not the convolutions, ends the step (profiles/r2_timeline_n2_single_comm_stream.txt).
+        self.opt_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("B200_COMM_PRIORITY", "-1"))) \
+            if os.environ.get("B200_SPLIT_COMM", "1") == "1" else self.comm_stream
         if self.world > 1 and not self.use_nccl:
             from ..parallel import topology
             from ..parallel.symm import SymmetricArena
@@ -187,8 +193,14 @@ class NativeEngine:
         # EXPERIMENTAL (--zero1): buckets that take a reduce-scatter algorithm run reduce-scatter +
         # Adam on the owned cells + all-gather of the new bf16 weights as ONE kernel; the fp32 master
         # and moments of a cell are then only current on its owner (prepare_export gathers them).
-        self.zero1 = bool(zero1) and self.arena is not None and self.arena.wire_dtype == BF16 \
-            and self.cross_group is None and optimizer == "adam"
+        # zero1: True / False, or "auto" = on from 4 ranks up (measured, profiles/r2_*: at 8 ranks it
+        # takes the step from 7.35 to 6.83 ms; at 2 ranks every rank still owns half of the optimizer
+        # state and the fused kernel's thin CTAs are slower than all-reduce + replicated Adam).
+        z1_ok = self.arena is not None and self.arena.wire_dtype == BF16 and self.cross_group is None \
+            and optimizer == "adam"
+        if zero1 == "auto":
+            zero1 = z1_ok and self.world >= 4
+        self.zero1 = bool(zero1) and z1_ok
         if zero1 and not self.zero1 and self.world > 1:
             raise ValueError("--zero1 needs Adam, the bf16 wire and all ranks in one NVLink domain")
         self._zero1_buckets: set = set()
@@ -587,11 +599,19 @@ class NativeEngine:
             # the owner rank only.
             if self.zero1 and self.apply_updates and prepacked and algo != "oneshot":
                 self._mark("z1_%d start" % bi, "comm")
+                zev0 = None
+                if self._comm_events is not None:
+                    zev0 = torch.cuda.Event(enable_timing=True)
+                    zev0.record()
                 self.arena.zero1_step(None if prepacked else self.g32, self.p32, self.m32, self.v32, self.w16,
                                       s, e - s, algo=algo, slot=bi % self.arena.slots, max_ctas=self.zero1_ctas,
                                       inv_world=1.0 / self.world, lr=self.lr, beta1=self.beta1, beta2=self.beta2,
                                       eps=self.eps, weight_decay=self.weight_decay, step=self.step_count)
                 self._zero1_buckets.add(bi)
+                if zev0 is not None:             # reduce-scatter + optimizer + all-gather: same wire bytes
+                    zev1 = torch.cuda.Event(enable_timing=True)
+                    zev1.record()
+                    self._comm_events.append((zev0, zev1, (e - s) * self.arena.wire.element_size()))
                 self._mark("z1_%d end" % bi, "comm")
                 return
             to_f32 = (algo == "oneshot" or self.unpack_fp32 or self.arena.wire_dtype == F32
@@ -612,12 +632,20 @@ class NativeEngine:
                 dist.all_reduce(self.g32[s:e] if to_f32 else self.arena.wire[s:e], group=self.cross_group)
             self._mark("ar%d end" % bi, "comm")
             if self.apply_updates:
-                self._apply_update(s, e, None if to_f32 else self.arena.wire[s:e],
-                                   zero=not (prepacked or self._bucket_store_only[bi]))
-                self._mark("opt%d end" % bi, "comm")
+                if self.opt_stream is not self.comm_stream:
+                    red = torch.cuda.Event()
+                    red.record()                      # on the comm stream: bucket bi is reduced
+                    self.opt_stream.wait_event(red)
+                with torch.cuda.stream(self.opt_stream):
+                    self._apply_update(s, e, None if to_f32 else self.arena.wire[s:e],
+                                       zero=not (prepacked or self._bucket_store_only[bi]))
+                    self._mark("opt%d end" % bi, "opt")
 
     def _end_step(self) -> None:
-        torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.comm_stream)
+        if self.opt_stream is not self.comm_stream:
+            cur.wait_stream(self.opt_stream)
 
     # ================================================================================ public
     def set_meter(self, meter: Optional[DeviceMeter]) -> None:
@@ -719,7 +747,8 @@ class NativeEngine:
         return {"wire_MB_per_step": round(nbytes / steps / 1e6, 2), "ms_per_step": round(ms / steps, 4),
                 "launches_per_step": len(self.plan.buckets), "bus_GBs": round(bus, 1),
                 "frac_of_770_measured": round(bus / 770.0, 3), "frac_of_900_nominal": round(bus / 900.0, 3),
-                "comm_ctas": self.comm_ctas, "overlapped_with_backward": True}
+                "comm_ctas": self.comm_ctas, "overlapped_with_backward": True,
+                "includes_fused_optimizer": bool(self._zero1_buckets)}
 
     def phase_times(self) -> Dict[str, float]:
         return self.timer.collect()

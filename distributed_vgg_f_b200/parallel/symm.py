@@ -18,8 +18,8 @@ import torch.distributed as dist
 from .. import ops
 
 ONESHOT_MAX_BYTES = 512 * 1024      # wire bytes below which the latency-optimal one-shot wins (no multicast)
-ONESHOT_MAX_BYTES_NVLS = 64 * 1024  # with NVLS the switch does the ws-way sum: it wins from ~32 KB at ws=8
-                                    # (profiles/r1_v4_allreduce_sweep_ws8.json)
+ONESHOT_MAX_BYTES_NVLS = 0          # with NVLS the switch does the ws-way sum: 16 us at EVERY size from 1 KB up at
+                                    # ws=8 against 21 us for one-shot (profiles/r2_allreduce_sweep_ws8.json)
 
 
 def owned_cells(start: int, n: int, G: int, world: int, rank: int):

@@ -93,8 +93,10 @@ def manage_training(args) -> Trainer:
                              compute_dtype=args.dtype, allreduce=args.allreduce,
                              wire_dtype=args.wire_dtype, bucket_mb=args.bucket_mb, seed=args.seed,
                              pretrained_state=pretrained, profile=args.profile,
-                             zero1=getattr(args, "zero1", False))
+                             zero1={"auto": "auto", "on": True, "off": False}[getattr(args, "zero1", "auto")])
         optimizer = None            # fused into the engine
+        if model.world > 1:
+            model.comm_timing(True)   # [Perf] line: all-reduce GB/s and fraction of the NVLink rate per epoch
     else:
         model = build_oracle(spec, seed=args.seed, pretrained_state=pretrained).to(device)
         if distributed_is_initialized():

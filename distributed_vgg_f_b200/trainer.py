@@ -80,14 +80,32 @@ class Trainer:
                 flush=True,
             )
             if self.verbose_throughput and train_loss.count:
-                print("[Perf] Epoch: {}/{}, train images/sec (this rank): {:.1f}{}".format(
+                print("[Perf] Epoch: {}/{}, train images/sec (this rank): {:.1f}{}{}".format(
                     epoch, epochs, train_loss.count / max(t1 - t0, 1e-9),
-                    self._utilisation(train_loss.count, t1 - t0)), flush=True)
+                    self._utilisation(train_loss.count, t1 - t0), self._comm_line()), flush=True)
+                ht = getattr(self, "epoch_host_times", None)
+                if ht:
+                    print("[Perf] Epoch: {}/{}, host: first batch after {:.1f} ms, steps enqueued in {:.1f} ms, "
+                          "GPU drained {:.1f} ms later; validation pass {:.1f} ms".format(
+                              epoch, epochs, ht["first_batch_ms"], ht["enqueue_ms"], ht["drain_ms"],
+                              1e3 * (time.perf_counter() - t1)), flush=True)
             self.history.append(dict(epoch=epoch, train_loss=train_loss.average,
                                      train_acc=train_acc.accuracy, test_loss=test_loss.average,
                                      test_acc=test_acc.accuracy))
             if self.on_epoch_end is not None:
                 self.on_epoch_end(epoch, self)
+
+    def _comm_line(self) -> str:
+        """Gradient all-reduce of the epoch as the step saw it: bus GB/s and fraction of the NVLink rate
+        (SURVEY 5.5).  Needs ``engine.comm_timing(True)`` (the CLI's --profile comm)."""
+        rep = getattr(self.model, "comm_report", None)
+        steps = len(self.train_loader) if hasattr(self.train_loader, "__len__") else 0
+        r = rep(max(steps, 1)) if rep is not None else None
+        if not r:
+            return ""
+        return ", grad all-reduce {:.0f} MB/step in {:.2f} ms = {:.0f} GB/s bus ({:.0f}% of 770 measured, {:.0f}% of 900 nominal)".format(
+            r["wire_MB_per_step"], r["ms_per_step"], r["bus_GBs"], 100 * r["frac_of_770_measured"],
+            100 * r["frac_of_900_nominal"])
 
     def _utilisation(self, images: int, seconds: float) -> str:
         """Native engine only: achieved training TFLOP/s (3 x forward FLOPs of the layer table) and
@@ -109,9 +127,16 @@ class Trainer:
         meter = DeviceMeter(self.device)
         if _is_native(self.model):
             self.model.set_meter(meter)
+            t0 = time.perf_counter()
+            first = None
             for batch in self.train_loader:
+                if first is None:
+                    first = time.perf_counter() - t0       # loader start-up: time to the first batch
                 self.model.train_step(batch)
+            t1 = time.perf_counter()
             self.model.sync()
+            self.epoch_host_times = {"first_batch_ms": 1e3 * (first or 0.0), "enqueue_ms": 1e3 * (t1 - t0),
+                                     "drain_ms": 1e3 * (time.perf_counter() - t1)}
             return meter.snapshot()
 
         self.model.train()

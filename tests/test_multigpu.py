@@ -45,7 +45,7 @@ def _allreduce_worker(rank, world, wire_fp32):
     from distributed_vgg_f_b200.parallel.symm import SymmetricArena
 
     dev = torch.device("cuda", rank)
-    n_max = 1 << 24
+    n_max = 1 << 23
     arena = SymmetricArena(n_max, dev, wire_dtype=torch.float32 if wire_fp32 else torch.bfloat16)
     algos = ["oneshot", "twoshot"] + (["nvls"] if arena.has_multicast else [])
     torch.manual_seed(100 + rank)
@@ -250,8 +250,15 @@ def test_allreduce_stress_mixed_slots_200():
 
 # ------------------------------------------------------------------- experimental: fused ZeRO-1 step
 def _zero1_worker(rank, world):
-    """--zero1 (reduce-scatter + Adam on owned cells + all-gather of bf16 weights in one kernel) against
-    the default path (fused all-reduce, replicated Adam) from the same weights on the same batches."""
+    """zero1 (reduce-scatter + Adam on owned cells + all-gather of bf16 weights in one kernel) against
+    the replicated path (fused all-reduce, Adam on every rank) from the same weights on the same batches.
+
+    Numerics of the comparison: conv / FC split-K partial sums are fp32 red.adds whose order depends on
+    the buffers' addresses and on what else is resident, so two engines are not bit-identical, and with
+    torch's eps = 1e-8 Adam's first steps are ~ lr * sign(g): a near-zero gradient whose sign flips moves
+    a weight by 2 lr and the trajectories drift apart chaotically (bench/debug_zero1.py; under identical
+    conditions the two paths ARE bit-identical).  The test therefore uses eps = 1, where the update is
+    smooth in g, and compares the fp32 optimizer state after three steps."""
     import torch.distributed as dist
 
     from distributed_vgg_f_b200.engine.native_engine import NativeEngine
@@ -260,30 +267,44 @@ def _zero1_worker(rank, world):
     dev = torch.device("cuda", rank)
     spec = vggf_mini_spec(3)
     init = build_oracle(spec, seed=0).state_dict()
-    kw = dict(device=dev, batch=4, lr=1e-3, seed=0, input_hw=64, init_state=init, allreduce="twoshot", bucket_mb=0.25)
+    kw = dict(zero1=False, device=dev, batch=4, lr=5e-2, seed=0, input_hw=64, init_state=init, allreduce="twoshot",
+              bucket_mb=0.25)
     ref = NativeEngine(spec, **kw)
-    z = NativeEngine(spec, zero1=True, **kw)
+    z = NativeEngine(spec, **dict(kw, zero1=True))
     assert z.zero1
+    p0 = ref.p32.clone()
     for e in (ref, z):
         e.train_dropout = False
+        e.eps = 1.0
     g = torch.Generator().manual_seed(7 + rank)
     for _ in range(3):
         x = torch.randn(4, 3, 64, 64, generator=g).to(torch.bfloat16).float()
         y = torch.randint(0, 3, (4,), generator=g)
-        ref.train_step((x, y))
-        z.train_step((x, y))
-    ref.sync(); z.sync()
+        for e in (ref, z):
+            e.train_step((x, y))
+            e.sync()
+            dist.barrier()
     assert z._zero1_buckets, "no bucket took the fused path"
-    # bf16 weights: identical up to FMA-contraction differences between the two Adam code paths
-    diff = (ref.w16.float() - z.w16.float()).abs()
-    assert float(diff.max()) <= 2e-2 * float(ref.w16.float().abs().max()) and float((diff > 0).float().mean()) < 1e-2
+    # every replica holds the same all-gathered bf16 weights
     w = z.w16.clone()
     dist.broadcast(w, src=0)
     assert torch.equal(w, z.w16), "replicas diverged"
     z.prepare_export()                                   # collective gather of the sharded fp32 state
-    assert float((ref.p32 - z.p32).abs().max()) < 1e-5 and float((ref.m32 - z.m32).abs().max()) < 1e-5
+
+    def rel(a, b):
+        return float((a - b).norm() / (b.norm() + 1e-30))
+
+    moved = rel(ref.p32, p0)
+    assert moved > 1e-4, "the optimizer did not move the weights (%g): vacuous test" % moved
+    for name, a, b in (("update", z.p32 - p0, ref.p32 - p0), ("exp_avg", z.m32, ref.m32), ("exp_avg_sq", z.v32, ref.v32)):
+        for bi, bk in enumerate(z.plan.buckets):
+            r = rel(a[bk.start:bk.end], b[bk.start:bk.end])
+            assert r < 2e-2, "%s of bucket %d (zero1=%s) differs: rel %g" % (name, bi, bi in z._zero1_buckets, r)
+    # the bf16 shadow every rank computes with IS the rounded fp32 master of the owner
+    for bi in sorted(z._zero1_buckets):
+        bk = z.plan.buckets[bi]
+        assert torch.equal(z.w16[bk.start:bk.end], z.p32[bk.start:bk.end].to(torch.bfloat16)), bi
 
 
-@pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL", "0") != "1", reason="experimental: set B200_EXPERIMENTAL=1")
 def test_zero1_fused_step_matches_replicated_adam():
     _run(_zero1_worker, 2)
