@@ -367,6 +367,24 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("cast_to_bf16", &cast_to_bf16);
   m.def("cast_to_f32", &cast_to_f32);
   m.def("cross_entropy", &cross_entropy);
+  m.def("head_ce_supported", [](int64_t B, int64_t C, int64_t K) { return b200::head_ce_supported((int)B, (int)C, (int)K); });
+  m.def("head_ce", [](const at::Tensor& h, const at::Tensor& W, const at::Tensor& bias, const at::Tensor& target,
+                      at::Tensor logits, c10::optional<at::Tensor> dlogits, int64_t ldd, c10::optional<at::Tensor> dW,
+                      c10::optional<at::Tensor> db, c10::optional<at::Tensor> dh, double drop_scale, bool relu,
+                      c10::optional<at::Tensor> meter, c10::optional<at::Tensor> loss_out,
+                      c10::optional<at::Tensor> class_weights) {
+    c10::cuda::CUDAGuard g(h.device());
+    TORCH_CHECK(h.dim() == 2 && W.dim() == 2 && h.size(1) == W.size(1) && h.is_contiguous() && W.is_contiguous(),
+                "head_ce: h [B][K], W [C][K], contiguous");
+    TORCH_CHECK(target.scalar_type() == at::kLong && logits.is_contiguous() && logits.size(0) == h.size(0) &&
+                logits.size(1) == W.size(0), "head_ce: int64 targets, logits [B][C]");
+    TORCH_CHECK(dW.has_value() == db.has_value(), "head_ce: dW and db come together");
+    b200::head_ce_fused(bfp(h), bfp(W), f32p(bias), reinterpret_cast<const long long*>(target.data_ptr()), f32p(logits),
+                        dlogits.has_value() ? bfp_mut(*dlogits) : nullptr, (int)ldd, f32p_opt(dW), f32p_opt(db),
+                        dh.has_value() ? bfp_mut(*dh) : nullptr, (float)drop_scale, relu, f32p_opt(meter),
+                        f32p_opt(loss_out), (int)h.size(0), (int)W.size(0), (int)h.size(1), f32p_opt(class_weights),
+                        cur_stream());
+  });
   m.def("adam", &adam);
   m.def("sgd", &sgd);
   m.def("augment", &augment);

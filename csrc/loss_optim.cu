@@ -96,6 +96,156 @@ void cross_entropy_fused(const float* logits, const long long* target, bf16* dlo
   check_last("cross_entropy_fused");
 }
 
+// ------------------------------------------------------------- fused head: last Linear + CE + bwd
+// K-FUN2+CE: the funnel's Linear(512, C) (distributedVggf.py:56), cross_entropy (:168),
+// Accuracy2 / Average (distributedUtil.py:95-96, :55-58) and the whole backward of that layer in ONE
+// launch of one CTA -- seven launches before (GEMM, bias epilogue, CE, bias grad, wgrad GEMM, dgrad
+// GEMM, ReLU/dropout-mask epilogue).  C <= 8 classes, K <= 1024 inputs, B <= 256 rows; everything lives
+// in shared memory / registers:
+//   logits[r][c] = bias[c] + sum_k h[r][k] W[c][k]            (warp per row, fp32 accumulation)
+//   loss, argmax == target count, B  -> device meter;  dlogits = (softmax - onehot) * w / norm -> bf16
+//   db[c] += sum_r dl[r][c];  dW[c][k] = sum_r dl[r][c] h[r][k];                (thread per k)
+//   dh[r][k] = (h[r][k] > 0) * drop_scale * sum_c dl[r][c] W[c][k]  -> bf16     (previous layer's dz)
+// Rounding points are those of the unfused path: dlogits are rounded to bf16 before they are used.
+constexpr int HEAD_MAXC = 8, HEAD_MAXK = 1024, HEAD_MAXB = 256, HEAD_THREADS = 512;
+
+__global__ void __launch_bounds__(HEAD_THREADS, 1)
+head_ce_kernel(const bf16* __restrict__ h, const bf16* __restrict__ W, const float* __restrict__ bias,
+               const long long* __restrict__ target, float* __restrict__ logits, bf16* __restrict__ dlogits, int ldd,
+               float* __restrict__ dW, float* __restrict__ db, bf16* __restrict__ dh, float drop_scale, int relu,
+               float* __restrict__ meter, float* __restrict__ loss_out, int B, int C, int K,
+               const float* __restrict__ cw) {
+  __shared__ float sW[HEAD_MAXC * HEAD_MAXK];
+  __shared__ float sdl[HEAD_MAXB * HEAD_MAXC];
+  __shared__ float s_loss[32], s_correct[32], s_wsum[32];
+  __shared__ float s_total_w;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < C * K; i += blockDim.x) sW[i] = __bfloat162float(W[i]);
+
+  float wsum_local = 0.f;
+  if (cw) {      // class weights: normaliser = sum_i w[target_i]   (same as cross_entropy_kernel)
+    for (int r = threadIdx.x; r < B; r += blockDim.x) wsum_local += cw[target[r]];
+    for (int o = 16; o; o >>= 1) wsum_local += __shfl_xor_sync(0xffffffffu, wsum_local, o);
+    if (lane == 0) s_wsum[warp] = wsum_local;
+  }
+  __syncthreads();
+  if (cw && threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < nwarps; ++i) t += s_wsum[i];
+    s_total_w = t;
+  }
+  __syncthreads();
+  const float norm = cw ? 1.f / s_total_w : 1.f / static_cast<float>(B);
+
+  // ---- forward + loss + dlogits ---------------------------------------------------------------
+  float loss_acc = 0.f, correct_acc = 0.f;
+  for (int r = warp; r < B; r += nwarps) {
+    float acc[HEAD_MAXC];
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c) acc[c] = 0.f;
+    const bf16* hr = h + static_cast<long long>(r) * K;
+    for (int k = lane; k < K; k += 32) {
+      const float hv = __bfloat162float(hr[k]);
+#pragma unroll
+      for (int c = 0; c < HEAD_MAXC; ++c)
+        if (c < C) acc[c] = fmaf(hv, sW[c * K + k], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c)
+      for (int o = 16; o; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    const int t = static_cast<int>(target[r]);
+    float mx = -INFINITY;
+    int amax = 0;
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c)
+      if (c < C) {
+        acc[c] += bias[c];
+        if (acc[c] > mx) { mx = acc[c]; amax = c; }       // first maximum, like torch.argmax
+      }
+    float se = 0.f, zt = 0.f;
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c)
+      if (c < C) {
+        se += __expf(acc[c] - mx);
+        if (c == t) zt = acc[c];
+      }
+    const float lse = mx + __logf(se);
+    const float w = cw ? cw[t] : 1.f;
+    if (lane < ldd || lane < C) {
+      float g = 0.f, z = 0.f;
+#pragma unroll
+      for (int c = 0; c < HEAD_MAXC; ++c)
+        if (c == lane && c < C) {
+          z = acc[c];
+          g = (__expf(acc[c] - lse) - (c == t ? 1.f : 0.f)) * w * norm;
+        }
+      if (lane < C) {
+        logits[static_cast<long long>(r) * C + lane] = z;
+        sdl[r * HEAD_MAXC + lane] = __bfloat162float(__float2bfloat16(g));
+      }
+      if (dlogits && lane < ldd) dlogits[static_cast<long long>(r) * ldd + lane] = __float2bfloat16(g);
+    }
+    if (lane == 0) {
+      loss_acc += w * (lse - zt);
+      correct_acc += (amax == t) ? 1.f : 0.f;
+    }
+  }
+  if (lane == 0) { s_loss[warp] = loss_acc; s_correct[warp] = correct_acc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tl = 0.f, tc = 0.f;
+    for (int i = 0; i < nwarps; ++i) { tl += s_loss[i]; tc += s_correct[i]; }
+    const float mean = cw ? tl / s_total_w : tl / static_cast<float>(B);
+    if (meter) {
+      atomicAdd(meter + 0, mean * static_cast<float>(B));
+      atomicAdd(meter + 1, tc);
+      atomicAdd(meter + 2, static_cast<float>(B));
+    }
+    if (loss_out) *loss_out = mean;
+  }
+  if (!dW) return;                       // evaluation: forward + metrics only
+
+  // ---- backward of the layer --------------------------------------------------------------------
+  if (threadIdx.x < C) {
+    float sum = 0.f;
+    for (int r = 0; r < B; ++r) sum += sdl[r * HEAD_MAXC + threadIdx.x];
+    db[threadIdx.x] += sum;
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float wk[HEAD_MAXC], gw[HEAD_MAXC];
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c) { wk[c] = c < C ? sW[c * K + k] : 0.f; gw[c] = 0.f; }
+    for (int r = 0; r < B; ++r) {
+      const float hv = __bfloat162float(h[static_cast<long long>(r) * K + k]);
+      float dx = 0.f;
+#pragma unroll
+      for (int c = 0; c < HEAD_MAXC; ++c)
+        if (c < C) {
+          const float g = sdl[r * HEAD_MAXC + c];
+          gw[c] = fmaf(g, hv, gw[c]);
+          dx = fmaf(g, wk[c], dx);
+        }
+      if (dh) dh[static_cast<long long>(r) * K + k] = __float2bfloat16((!relu || hv > 0.f) ? dx * drop_scale : 0.f);
+    }
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c)
+      if (c < C) dW[static_cast<long long>(c) * K + k] = gw[c];
+  }
+}
+
+bool head_ce_supported(int B, int C, int K) { return C <= HEAD_MAXC && K <= HEAD_MAXK && B <= HEAD_MAXB && B > 0; }
+
+void head_ce_fused(const bf16* h, const bf16* W, const float* bias, const long long* target, float* logits,
+                   bf16* dlogits, int ldd, float* dW, float* db, bf16* dh, float drop_scale, bool relu, float* meter,
+                   float* loss_out, int B, int C, int K, const float* class_weights, cudaStream_t s) {
+  if (!head_ce_supported(B, C, K)) throw std::runtime_error("[b200] head_ce_fused: needs C <= 8, K <= 1024, B <= 256");
+  if (ldd > 32) throw std::runtime_error("[b200] head_ce_fused: dlogits row stride must be <= 32");
+  head_ce_kernel<<<1, HEAD_THREADS, 0, s>>>(h, W, bias, target, logits, dlogits, ldd, dW, db, dh, drop_scale,
+                                            relu ? 1 : 0, meter, loss_out, B, C, K, class_weights);
+  count_launch();
+  check_last("head_ce_fused");
+}
+
 // ---------------------------------------------------------------------------------------- Adam
 // One pass over the flat arena: read grad (fp32 local or bf16 reduced wire), update fp32 master
 // weight and both moments, emit the bf16 shadow used by the GEMMs, and zero the fp32 gradient so

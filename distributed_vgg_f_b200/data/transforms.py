@@ -151,3 +151,22 @@ def reference_transforms(train: bool):
             norm,
         ])
     return T.Compose([T.Resize(size=DATA.resize), T.CenterCrop(size=DATA.crop), T.ToTensor(), norm])
+
+
+def torchvision_chain_fixed(img_hwc_u8, params_row, resize: int = DATA.resize, crop: int = DATA.crop) -> torch.Tensor:
+    """The reference's TRAIN pipeline (distributedVggf.py:88-95) with its random draws pinned to one row
+    of ``sample_train_params``: torchvision's own functional ops on a PIL image --
+    resized_crop(bilinear) -> rotate(nearest, zero fill) -> hflip -> center_crop -> to_tensor -> normalize.
+    Used by the parity tests of ``augment_reference`` and of the sm_100a augment kernel."""
+    from PIL import Image
+    from torchvision.transforms import InterpolationMode
+    from torchvision.transforms import functional as TF
+
+    top, left, ch, cw, c, s, flip = [float(v) for v in params_row[:7]]
+    img = Image.fromarray(img_hwc_u8.numpy() if isinstance(img_hwc_u8, torch.Tensor) else img_hwc_u8)
+    img = TF.resized_crop(img, int(top), int(left), int(ch), int(cw), [resize, resize], InterpolationMode.BILINEAR)
+    img = TF.rotate(img, math.degrees(math.atan2(s, c)), InterpolationMode.NEAREST, fill=0)
+    if flip > 0.5:
+        img = TF.hflip(img)
+    img = TF.center_crop(img, [crop, crop])
+    return TF.normalize(TF.to_tensor(img), list(DATA.mean), list(DATA.std))

@@ -325,6 +325,12 @@ class NativeEngine:
         self.logits = torch.zeros(B, spec.num_classes, dtype=F32, device=dev)
         self.loss_buf = torch.zeros(1, dtype=F32, device=dev)
         self.scratch_meter = torch.zeros(4, dtype=F32, device=dev)
+        # K-FUN2+CE: last Linear + cross-entropy + metrics + that layer's backward as ONE launch when the
+        # head is small (the funnel: 512 -> C <= 8); VGG-16/1000 keeps the GEMM path.  B200_FUSED_HEAD=0: off.
+        lastf = spec.fcs[-1]
+        self.fused_head = (os.environ.get("B200_FUSED_HEAD", "1") == "1" and len(spec.fcs) >= 2
+                           and bool(ops.require().head_ce_supported(B, lastf.fout, lastf.fin)))
+        self._head_in = None
         # backward activations-gradients: two ping-pong buffers big enough for the largest map
         biggest = max(a.numel() for a in self.acts)
         self.dbuf = [torch.empty(biggest, dtype=BF16, device=dev) for _ in range(2)]
@@ -429,6 +435,9 @@ class NativeEngine:
         h = x.reshape(b, -1)
         last = len(spec.fcs) - 1
         for i, f in enumerate(spec.fcs):
+            if i == last and self.fused_head:
+                self._head_in = h            # logits, loss and this layer's backward: _head()
+                break
             m_tiles = (f.fout + 127) // 128
             ks = self._ksplit(m_tiles, (f.fin + 63) // 64)
             acc = self.fc_acc[i][:b]
@@ -440,6 +449,27 @@ class NativeEngine:
                 ops.fc_bias_act(acc, self._b(f.name), self.fc_y[i][:b], None, B=b, N=f.fout, relu=f.relu,
                                 drop_p=p, seed=self._drop_key(i), offset=self.step_count)
                 h = self.fc_y[i][:b]
+
+    def _loss(self, b: int, train: bool) -> None:
+        """Loss + metrics (+ dlogits when training) from the forward state."""
+        meter = self.meter.buf if self.meter is not None else self.scratch_meter
+        if not self.fused_head:
+            ld = self.fc_dz[-1].shape[1]
+            ops.cross_entropy(self.logits[:b], self.labels_dev[:b], self.fc_dz[-1][:b] if train else None,
+                              ld if train else 0, meter, self.loss_buf,
+                              class_weights=self.class_weights if train else None)   # like the reference's loops
+            return
+        f, prev = self.spec.fcs[-1], self.spec.fcs[-2]
+        C = ops.require()
+        if train:
+            p = prev.dropout if self.train_dropout else 0.0
+            C.head_ce(self._head_in, self._w(f.name), self._b(f.name), self.labels_dev[:b], self.logits[:b],
+                      self.fc_dz[-1][:b], self.fc_dz[-1].shape[1], self._grad(f.name + ".weight"),
+                      self._grad(f.name + ".bias"), self.fc_dz[-2][:b], 1.0 / (1.0 - p), bool(prev.relu), meter,
+                      self.loss_buf, self.class_weights)
+        else:
+            C.head_ce(self._head_in, self._w(f.name), self._b(f.name), self.labels_dev[:b], self.logits[:b],
+                      None, 0, None, None, None, 1.0, False, meter, self.loss_buf, None)
 
     # ============================================================================== backward
     def _grad(self, name: str) -> torch.Tensor:
@@ -453,6 +483,11 @@ class NativeEngine:
         # ---- FC stack ----------------------------------------------------------------------
         for i in range(last, -1, -1):
             f = fcs[i]
+            if i == last and self.fused_head:     # produced by _loss(): gradients are already in the arena
+                self._bucket_done(f.name + ".bias")
+                self._bucket_done(f.name + ".weight")
+                self._mark("bwd " + f.name)
+                continue
             ld = self.fc_dz[i].shape[1]
             dz = self.fc_dz[i][:b]                                   # [b][ld] bf16, cols >= fout are 0
             x_in = self.fc_y[i - 1][:b] if i > 0 else self.feat.reshape(b, -1)
@@ -668,10 +703,7 @@ class NativeEngine:
         self._mark("input")
         t.start("forward")
         self._forward(b, train=True)
-        ld = self.fc_dz[-1].shape[1]
-        meter = self.meter.buf if self.meter is not None else self.scratch_meter
-        ops.cross_entropy(self.logits[:b], self.labels_dev[:b], self.fc_dz[-1][:b], ld, meter, self.loss_buf,
-                          class_weights=self.class_weights)
+        self._loss(b, train=True)
         self._release_input()
         self._mark("loss")
         t.stop("forward")
@@ -688,14 +720,18 @@ class NativeEngine:
     def eval_step(self, batch) -> torch.Tensor:
         b = self._stage_input(batch)
         self._forward(b, train=False)
-        meter = self.meter.buf if self.meter is not None else self.scratch_meter
-        ops.cross_entropy(self.logits[:b], self.labels_dev[:b], None, 0, meter, self.loss_buf)
+        self._loss(b, train=False)
         self._release_input()
         return self.loss_buf
 
     def forward_logits(self, batch) -> torch.Tensor:
         b = self._stage_input(batch)
         self._forward(b, train=False)
+        if self.fused_head:          # the logits come out of the fused head kernel
+            keep = self.meter
+            self.meter = None
+            self._loss(b, train=False)
+            self.meter = keep
         self._release_input()
         return self.logits[:b].clone()
 

@@ -201,3 +201,26 @@ def test_cli_native_end_to_end(tmp_path, capsys):
     assert cli.main(base + ["-ep", "3", "--resume", ck]) == 0
     out = capsys.readouterr().out
     assert "resumed from" in out and "[Info] Epoch: 3/3," in out and "Epoch: 1/3" not in out
+
+
+def test_pretrained_state_reaches_the_native_arenas(tmp_path):
+    """--pretrained on the native path: a torchvision VGG-16 state dict lands in the engine's arenas
+    (OHWI conv weights, NHWC-ordered FC-1 columns) and comes back out in torch layout unchanged, while
+    the funnel keeps its fresh init (distributedVggf.py:46-57)."""
+    import torchvision
+
+    from distributed_vgg_f_b200.engine.native_engine import NativeEngine
+    from distributed_vgg_f_b200.models.vggf import build_oracle, vggf_spec
+
+    tv = torchvision.models.vgg16(weights=None).state_dict()
+    spec = vggf_spec(3)
+    eng = NativeEngine(spec, device=torch.device(DEV), batch=2, seed=4, pretrained_state=tv, distributed=False)
+    out = eng.export_state()
+    fresh = build_oracle(spec, seed=4).state_dict()
+    for k, v in out.items():
+        if k.startswith("classifier.6."):
+            assert torch.equal(v, fresh[k]), k
+        else:
+            assert torch.equal(v, tv[k].float()), k
+    # and the bf16 shadow the kernels read is the rounded master
+    assert torch.equal(eng.w16, eng.p32.to(torch.bfloat16))

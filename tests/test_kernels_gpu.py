@@ -416,3 +416,75 @@ def test_augment_matches_reference():
     unf = F.unfold(got, 3, padding=1).view(4, 3, 9, 224 * 224).permute(0, 3, 2, 1).reshape(-1, 27)
     assert torch.equal(col[:, :27].float(), unf)
     assert torch.count_nonzero(col[:, 27:]) == 0
+
+
+def test_augment_kernel_matches_torchvision_chain():
+    """The sm_100a input kernel against torchvision's OWN transform ops on PIL images with the same draws
+    (distributedVggf.py:88-95) -- not against this repo's torch oracle."""
+    ops = _ops()
+    import numpy as np
+
+    from distributed_vgg_f_b200.data import transforms as T
+    from distributed_vgg_f_b200.data.synthetic import synthetic_uint8_batch
+
+    imgs, _ = synthetic_uint8_batch(4, 128, seed=13)
+    rng = np.random.default_rng(1)
+    imgs = np.clip(imgs.astype(np.int16) + rng.integers(-20, 20, imgs.shape), 0, 255).astype(np.uint8)
+    params = T.sample_train_params(4, 128, 128, torch.Generator().manual_seed(9))
+    params[0, 6], params[1, 6] = 0.0, 1.0
+    out = torch.empty(4, 224, 224, 4, dtype=torch.bfloat16, device=DEV)
+    ops.augment(torch.from_numpy(imgs).to(DEV), params.to(DEV), out, (256, 256), mode="nhwc", pad=4)
+    got = out[..., :3].float().permute(0, 3, 1, 2).cpu()
+    for i in range(4):
+        theirs = T.torchvision_chain_fixed(imgs[i], params[i])
+        d = (got[i] - theirs).abs()
+        # PIL's uint8 rounding of the resized image (0.009 after Normalize) + bf16 output rounding (2^-8 relative)
+        assert float((d < 0.04).float().mean()) > 0.995, (i, float((d < 0.04).float().mean()), float(d.max()))
+        assert float(d.mean()) < 0.012, (i, float(d.mean()))
+
+
+# ------------------------------------------------------------------ fused head (K-FUN2+CE)
+@pytest.mark.parametrize("B,C,K,weighted", [(64, 3, 512, False), (37, 5, 96, False), (64, 3, 512, True), (1, 8, 1024, False)])
+def test_head_ce_fused_matches_torch(B, C, K, weighted):
+    """Last Linear + cross-entropy + metrics + the layer's backward in one launch (loss_optim.cu::head_ce_kernel)
+    against plain torch fp32 with the same rounding points (bf16 operands, dlogits rounded to bf16)."""
+    from distributed_vgg_f_b200 import ops
+
+    Cx = ops.require()
+    g = torch.Generator(device="cuda").manual_seed(B * 131 + C)
+    h = torch.relu(torch.randn(B, K, device="cuda", generator=g)).to(torch.bfloat16)       # post-ReLU: has zeros
+    W = (torch.randn(C, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(C, device="cuda", generator=g) * 0.1
+    y = torch.randint(0, C, (B,), device="cuda", generator=g)
+    cw = (torch.rand(C, device="cuda", generator=g) + 0.5) if weighted else None
+    logits = torch.empty(B, C, device="cuda")
+    dl = torch.full((B, 8), 7.0, device="cuda", dtype=torch.bfloat16)
+    dW = torch.empty(C, K, device="cuda")
+    db = torch.ones(C, device="cuda")                   # accumulated into
+    dh = torch.empty(B, K, device="cuda", dtype=torch.bfloat16)
+    meter = torch.zeros(4, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    Cx.head_ce(h, W, bias, y, logits, dl, 8, dW, db, dh, 2.0, True, meter, loss, cw)
+
+    z = h.float() @ W.float().t() + bias
+    ref_loss = torch.nn.functional.cross_entropy(z, y, weight=cw)
+    wt = cw[y] if weighted else torch.ones(B, device="cuda")
+    norm = wt.sum() if weighted else torch.tensor(float(B), device="cuda")
+    g_ref = ((torch.softmax(z, 1) - torch.nn.functional.one_hot(y, C).float()) * wt[:, None] / norm)
+    g_bf = g_ref.to(torch.bfloat16).float()
+    torch.testing.assert_close(logits, z, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(loss[0], ref_loss, rtol=1e-4, atol=1e-5)
+    assert float(meter[1]) == float((z.argmax(1) == y).sum()) and float(meter[2]) == B
+    torch.testing.assert_close(meter[0], ref_loss * B, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dl[:, :C].float(), g_bf, rtol=0, atol=1e-6 + 8e-3 * float(g_ref.abs().max()))
+    assert float(dl[:, C:].float().abs().max()) == 0.0 if C < 8 else True
+    used = dl[:, :C].float()                            # what the kernel itself rounded
+    torch.testing.assert_close(dW, used.t() @ h.float(), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(db, 1.0 + used.sum(0), rtol=1e-4, atol=1e-6)
+    dh_ref = ((used @ W.float()) * (h.float() > 0) * 2.0).to(torch.bfloat16)
+    torch.testing.assert_close(dh.float(), dh_ref.float(), rtol=1e-2, atol=1e-6)
+    # evaluation form: forward + metrics only
+    logits2 = torch.empty_like(logits)
+    Cx.head_ce(h, W, bias, y, logits2, None, 0, None, None, None, 1.0, False, None, loss, None)
+    torch.testing.assert_close(logits2, z, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(loss[0], torch.nn.functional.cross_entropy(z, y), rtol=1e-4, atol=1e-5)

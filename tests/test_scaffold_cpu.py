@@ -515,3 +515,55 @@ def test_predict_tool_reproduces_validation_accuracy(synth_root, tmp_path, capsy
     assert P.main([ck, files[0], "--classes", "edible,other,toy", "--engine", "oracle"]) == 0
     line = capsys.readouterr().out.strip().split("\t")
     assert line[0] == files[0] and line[1] in ("edible", "other", "toy") and 0.0 < float(line[2]) <= 1.0
+
+
+# ------------------------------------------------------------------ parity with torchvision itself
+def test_train_augment_matches_torchvision_chain_on_fixed_draws():
+    """The fused train transform (one coordinate chain per output pixel) against torchvision's OWN ops
+    applied one after the other on a PIL image with the same drawn parameters (distributedVggf.py:88-95):
+    RandomResizedCrop(256, scale=(.8, 1)) -> RandomRotation(10) -> RandomHorizontalFlip -> CenterCrop(224)
+    -> ToTensor -> Normalize.  PIL rounds the resized image to uint8 before rotating (<= 0.5/255 per pixel,
+    0.009 after Normalize) and nearest-neighbour rotation can pick the neighbouring pixel when a coordinate
+    lands within float rounding of a pixel edge, hence "almost all pixels within 0.03"."""
+    import numpy as np
+
+    from distributed_vgg_f_b200.data import transforms as T
+    from distributed_vgg_f_b200.data.synthetic import synthetic_uint8_batch
+
+    imgs, _ = synthetic_uint8_batch(6, 128, 3, seed=11)
+    rng = np.random.default_rng(0)
+    imgs = np.clip(imgs.astype(np.int16) + rng.integers(-20, 20, imgs.shape), 0, 255).astype(np.uint8)   # texture
+    params = T.sample_train_params(6, 128, 128, torch.Generator().manual_seed(5))
+    # make sure both flip states and both rotation signs are exercised
+    params[0, 6], params[1, 6] = 0.0, 1.0
+    params[2, 4], params[2, 5] = math.cos(math.radians(9.5)), math.sin(math.radians(9.5))
+    params[3, 4], params[3, 5] = math.cos(math.radians(-9.5)), math.sin(math.radians(-9.5))
+    ours = T.augment_reference(torch.from_numpy(imgs), params, (256, 256))
+    for i in range(6):
+        theirs = T.torchvision_chain_fixed(imgs[i], params[i])
+        d = (ours[i] - theirs).abs()
+        frac_close = float((d < 0.03).float().mean())
+        assert frac_close > 0.995, (i, frac_close, float(d.max()))
+        assert float(d.mean()) < 0.008, (i, float(d.mean()))   # 0.25/255/std from PIL's uint8 rounding alone is 0.0043
+
+
+def test_pretrained_vgg16_state_is_loaded_like_the_reference(tmp_path):
+    """--pretrained (offline stand-in for models.vgg16(pretrained=True), distributedVggf.py:46): features.*
+    and classifier.0 / .3 come from the torchvision VGG-16 file, the funnel (classifier.6.0 / 6.3,
+    distributedVggf.py:52-57) keeps its fresh init -- exactly what the reference's factory produces."""
+    import torchvision
+
+    from distributed_vgg_f_b200 import vgg_funnel_model
+
+    tv = torchvision.models.vgg16(weights=None)
+    path = str(tmp_path / "vgg16.pth")
+    torch.save(tv.state_dict(), path)
+    fresh = vgg_funnel_model(3, seed=1).state_dict()
+    got = vgg_funnel_model(3, pretrained_path=path, seed=1).state_dict()
+    tvs = tv.state_dict()
+    for k, v in got.items():
+        if k.startswith("features.") or k.startswith("classifier.0.") or k.startswith("classifier.3."):
+            assert torch.equal(v, tvs[k]), k
+        else:                                    # the funnel head is not in the file
+            assert k.startswith("classifier.6.") and torch.equal(v, fresh[k]), k
+    assert "classifier.6.weight" in tvs and "classifier.6.weight" not in got
