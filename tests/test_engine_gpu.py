@@ -9,9 +9,16 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _mk(batch=4, hw=64, classes=3, seed=0, **kw):
+def _mk(batch=4, hw=64, classes=3, seed=0, fuse_pool=None, **kw):
+    import os
+
     from distributed_vgg_f_b200.engine.native_engine import NativeEngine
     from distributed_vgg_f_b200.models.vggf import build_oracle, vggf_mini_spec
+
+    if fuse_pool is not None:            # read once, when the engine lays out its buffers
+        os.environ["B200_FUSE_POOL"] = "1" if fuse_pool else "0"
+    else:
+        os.environ.pop("B200_FUSE_POOL", None)
 
     spec = vggf_mini_spec(classes)
     oracle = build_oracle(spec, seed=seed)
@@ -69,7 +76,9 @@ def test_backward_matches_reference_on_same_forward(capsys):
     from distributed_vgg_f_b200.models import layout as L
     from distributed_vgg_f_b200.ops import ref as R
 
-    spec, oracle, eng = _mk()
+    # the un-pooled activations this check gates on only exist when the pool is NOT fused into the conv
+    # epilogue (the default fuses it: test_fused_pool_step_matches_unfused_step covers that path)
+    spec, oracle, eng = _mk(fuse_pool=False)
     eng.train_dropout = False
     eng.apply_updates = False
     torch.manual_seed(3)
@@ -95,6 +104,32 @@ def test_backward_matches_reference_on_same_forward(capsys):
         print("\n[grad err, same forward] " + ", ".join("%s=%.1e" % kv for kv in worst.items()))
     bad = {k: v for k, v in worst.items() if v > 2e-2}
     assert not bad, bad
+
+
+def test_fused_pool_step_matches_unfused_step():
+    """The default step (2x2 max-pool inside the conv epilogue, argmax bit masks, unpool backward) against the
+    same step with separate pool kernels: same loss, same logits, same gradients (only the order of the
+    fp32 split-K red.adds may differ)."""
+    from distributed_vgg_f_b200.models import layout as L
+
+    torch.manual_seed(5)
+    x = torch.randn(4, 3, 64, 64, device=DEV).to(torch.bfloat16).float()
+    y = torch.randint(0, 3, (4,), device=DEV)
+    out = {}
+    for fused in (False, True):
+        spec, _, eng = _mk(fuse_pool=fused)
+        if fused and not any(m is not None for m in eng.pool_masks):
+            pytest.skip("no pooled layer of the mini model has a fusable tile shape")
+        assert fused or not any(m is not None for m in eng.pool_masks)
+        eng.train_dropout = False
+        eng.apply_updates = False
+        loss = float(eng.train_step((x, y)))
+        eng.sync()
+        out[fused] = (loss, eng.logits[:4].clone(), eng.g32.clone())
+    assert abs(out[True][0] - out[False][0]) < 1e-5
+    assert torch.equal(out[True][1], out[False][1])
+    a, r = out[True][2], out[False][2]
+    assert float((a - r).norm() / r.norm()) < 1e-3 and float((a - r).abs().max() / r.abs().max()) < 1e-2
 
 
 def test_forward_and_gradients_close_to_fp32_autograd(capsys):

@@ -8,7 +8,8 @@ equal, and the comparison is about the arithmetic.
 
 What is asserted (numbers measured on a B200 are recorded in profiles/r2_fullscale_parity.json):
   * step-1 gradients, tensor by tensor, against fp32 autograd of the reference model (TF32 off):
-    cosine similarity and relative L2 error;
+    cosine similarity and relative L2 error (>= 0.99 for the classifier and the last conv block, >= 0.97 down
+    to the first convolution: see the comment at the assertions for why it decays with depth);
   * the per-step training loss of 50 optimisation steps against the reference's loop from the same
     weights (Adam, lr 1e-5 as in the reference's README);
   * both runs learn the synthetic classes.
@@ -146,11 +147,21 @@ def test_fullscale_loss_curve_and_gradients_match_reference_trainer(ref_module):
         pass
     print(json.dumps({k: report[k] for k in ("loss_step1", "max_abs_loss_diff", "mean_abs_loss_diff", "min_cos", "max_rel_l2")}))
     worst = sorted(grads.items(), key=lambda kv: kv[1]["cos"])[:4]
-    # gradients: bf16 activations / weights against fp32 -- direction and size agree tensor by tensor
-    assert report["min_cos"] >= 0.99, "step-1 gradient cosine below 0.99: %s" % worst
-    assert report["max_rel_l2"] <= 0.15, "step-1 gradient relative L2 error above 15%%: %s" % worst
-    # loss curve: same starting loss, same trajectory
-    assert abs(native_loss0 - float(loss0)) <= 0.02 * max(1.0, float(loss0))
-    assert report["mean_abs_loss_diff"] <= 0.03 and report["max_abs_loss_diff"] <= 0.12, (ref_losses, nat_losses)
+    # Gradients.  Measured on a B200 (profiles/r2_fullscale_parity.json): cosine 1.0000 at the head, 0.995 at
+    # classifier.0 / features.28, falling smoothly to 0.978 at features.0 (relative L2 error 0.001 -> 0.21).
+    # The growth with depth is ReLU / max-pool GATE FLIPS, not arithmetic error: a pre-activation within bf16
+    # rounding distance of zero (~0.3 % of them per layer) is on one side of the gate here and on the other in
+    # fp32, which moves a whole gradient entry, and every layer below inherits it (relative error ~ sqrt(flipped
+    # fraction) per layer, accumulating in quadrature over the 13 gated layers).  With the gates pinned to the same
+    # forward values the two backward passes agree to < 2 % everywhere (test_backward_matches_reference_on_same_
+    # forward), and the loss curves below coincide -- the noise is unbiased.
+    assert report["min_cos"] >= 0.97, "step-1 gradient cosine below 0.97: %s" % worst
+    assert report["max_rel_l2"] <= 0.25, "step-1 gradient relative L2 error above 25%%: %s" % worst
+    for name, v in grads.items():
+        if name.startswith("classifier.") or name.startswith("features.28"):
+            assert v["cos"] >= 0.99, (name, v)
+    # loss curve: same starting loss (measured: 6e-6 apart), same trajectory (measured: mean 7e-4, max 3.6e-3)
+    assert abs(native_loss0 - float(loss0)) <= 1e-3 * max(1.0, float(loss0))
+    assert report["mean_abs_loss_diff"] <= 0.005 and report["max_abs_loss_diff"] <= 0.02, (ref_losses, nat_losses)
     # and both learn
     assert sum(ref_losses[-5:]) / 5 < 0.8 * ref_losses[0] and sum(nat_losses[-5:]) / 5 < 0.8 * nat_losses[0]
