@@ -32,7 +32,7 @@ def to_us(v, unit):
     return num(v) * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3, "second": 1e6}.get(unit, 1)
 
 
-print("| kernel | grid x block | time us | DRAM read+write MB | achieved GB/s (% of measured %.0f) | dram %% | tensor pipe %% | l1tex %% | L2 %% | achieved occ %% | regs |"
+print("| kernel | grid x block | time us | DRAM read+write MB | achieved GB/s (%% of the measured %.0f GB/s) | dram %% | tensor pipe %% | l1tex %% | L2 %% | achieved occ %% | regs |"
       % peaks.get("hbm_gbs", 6567.0))
 print("|---|---|---|---|---|---|---|---|---|---|---|")
 for r in data:

@@ -60,14 +60,21 @@ def main():
     names = [(n, lane) for n, lane, _ in runs[0]]
     med = [statistics.median(r[i][2] for r in runs) for i in range(len(names))]
     rows = [{"name": n, "lane": lane, "ms": round(m, 4)} for (n, lane), m in zip(names, med)]
-    # every rank's step end -> max over ranks
+    # every rank's step end -> max over ranks; and the per-rank skew: when did each rank's LAST weight gradient
+    # finish (its own speed) and when did its step end (after the last bucket's reduction, which needs everybody)
     t_end = torch.tensor([rows[-1]["ms"]], device=dev)
+    last_w = max(r["ms"] for r in rows if r["lane"] == "compute" and r["name"].startswith("bwd "))
+    per_rank = torch.zeros(world, 2, device=dev)
+    per_rank[rank, 0], per_rank[rank, 1] = last_w, rows[-1]["ms"]
     if world > 1:
         dist.all_reduce(t_end, op=dist.ReduceOp.MAX)
+        dist.all_reduce(per_rank)
     if rank == 0:
         os.makedirs("gpurun_out", exist_ok=True)
         out = "gpurun_out/timeline_n%d%s.json" % (world, a.tag)
-        json.dump({"world": world, "comm_ctas": a.comm_ctas, "rows": rows, "step_end_max_over_ranks_ms": float(t_end)},
+        json.dump({"world": world, "comm_ctas": a.comm_ctas, "rows": rows, "step_end_max_over_ranks_ms": float(t_end),
+                   "per_rank_last_wgrad_ms": [round(float(v), 4) for v in per_rank[:, 0]],
+                   "per_rank_step_end_ms": [round(float(v), 4) for v in per_rank[:, 1]]},
                   open(out, "w"), indent=1)
         comp = [r for r in rows if r["lane"] == "compute"]
         comm = [r for r in rows if r["lane"] != "compute"]
@@ -79,6 +86,11 @@ def main():
         print("side streams (comm = reductions, opt = optimizer):")
         for r in comm:
             print("  %-5s %-28s %8.3f" % (r["lane"], r["name"], r["ms"]))
+        if world > 1:
+            lw = [float(v) for v in per_rank[:, 0]]
+            print("per-rank end of backward (ms): " + " ".join("%.3f" % v for v in lw)
+                  + "  -> spread %.3f ms: the last bucket's reduction cannot finish before the slowest rank's" % (max(lw) - min(lw)))
+            print("per-rank step end (ms):        " + " ".join("%.3f" % float(v) for v in per_rank[:, 1]))
         last_w = max(r["ms"] for r in comp if r["name"].startswith("bwd "))
         print("last wgrad enqueued-done at %.3f ms, step end (joined comm) at %.3f ms -> exposed tail %.3f ms"
               % (last_w, comp[-1]["ms"], comp[-1]["ms"] - last_w))
