@@ -118,9 +118,16 @@ def _engine_worker(rank, world, algo, expect_mode="flat"):
     eng.train_step((x[4 * rank:4 * rank + 4], y[4 * rank:4 * rank + 4]))
     eng.sync()
     import torch.distributed as dist
+    # what every replica computes with: the bf16 weights (all buckets) ...
+    w = eng.w16.clone()
+    dist.broadcast(w, src=0)
+    assert torch.equal(w, eng.w16), "replicas diverged after an update (bf16 weights)"
+    # ... and the fp32 master.  Under ZeRO-1 (default from 4 ranks up) the master of an FC-weight cell is
+    # current on its owner only: gather it first, as a checkpoint does.
+    eng.prepare_export()
     ref = eng.p32.clone()
     dist.broadcast(ref, src=0)
-    assert torch.equal(ref, eng.p32), "replicas diverged after an update"
+    assert torch.equal(ref, eng.p32), "replicas diverged after an update (fp32 master)"
 
 
 @pytest.mark.parametrize("algo", ["auto", "twoshot", "oneshot"])
