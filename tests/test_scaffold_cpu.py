@@ -187,6 +187,38 @@ def test_bucket_plan_covers_arena_and_splits_big_tensors():
         assert plan.buckets[ids[-1]].end >= plan.offsets[n] + plan.numels[n]
 
 
+def test_bucket_plan_late_caps_and_tail_bucket():
+    """The engine's plan: big messages for the FC weights that are ready first, one bucket per big conv
+    layer afterwards, and a small final bucket (its reduction + update is the only exposed part of the
+    gradient exchange)."""
+    from distributed_vgg_f_b200.models import layout as L
+
+    spec = vggf_spec(3)
+    order = L.ready_order(spec)
+    first_conv = next(n for n, _ in order if n.startswith("features."))
+    cap = 8 * 1024 * 1024
+    plan = make_bucket_plan(order, cap_elems=cap, late_cap_elems=int(9.5 * 1024 * 1024 / 4), late_from=first_conv,
+                            tail_elems=int(2400 * 1024 / 4))
+    assert plan.buckets[0].start == 0 and plan.buckets[-1].end == plan.total
+    assert all(a.end == b.start for a, b in zip(plan.buckets, plan.buckets[1:]))
+    assert all(b.start % plan.align == 0 and b.end % plan.align == 0 for b in plan.buckets)
+    conv_b = [b for b in plan.buckets if all(t.startswith("features.") for t in b.tensors)]
+    fc_b = [b for b in plan.buckets if b not in conv_b]
+    assert max(b.numel for b in fc_b) == cap                                   # 16.8 MB of bf16 wire
+    assert max(b.numel for b in conv_b) <= int(9.5 * 1024 * 1024 / 4) + plan.align
+    tail = plan.buckets[-1]
+    assert tail.tensors[-1] == "features.0.weight" and tail.numel * 2 < 1.3e6   # ~1.1 MB of bf16 wire
+    assert "features.10.weight" in tail.tensors and "features.12.weight" not in tail.tensors
+    # the five 512-channel layers' weights each sit in a bucket of their own size class (one layer per bucket)
+    for name in ("features.28.weight", "features.26.weight", "features.24.weight", "features.21.weight", "features.19.weight"):
+        (bi,) = plan.bucket_of(name)
+        assert sum(t.endswith(".weight") for t in plan.buckets[bi].tensors) == 1
+    # default arguments reproduce the plain capped plan
+    plain = make_bucket_plan(order, cap_elems=cap)
+    assert [(b.start, b.end) for b in plain.buckets] == \
+        [(b.start, b.end) for b in make_bucket_plan(order, cap_elems=cap, late_cap_elems=0, tail_elems=0).buckets]
+
+
 # ------------------------------------------------------------------------------------ checkpoint
 def test_checkpoint_layout_roundtrip(tmp_path):
     from distributed_vgg_f_b200.utils import checkpoint as ck
@@ -567,3 +599,27 @@ def test_pretrained_vgg16_state_is_loaded_like_the_reference(tmp_path):
         else:                                    # the funnel head is not in the file
             assert k.startswith("classifier.6.") and torch.equal(v, fresh[k]), k
     assert "classifier.6.weight" in tvs and "classifier.6.weight" not in got
+
+
+def test_resume_behind_an_lr_step_boundary_keeps_the_decayed_rate(synth_root, tmp_path):
+    """--lr-step decays the rate at epochs that are multiples of the step.  A run resumed BEHIND such a boundary
+    must continue at the decayed rate on both back ends (round-1 ADVICE: the native engine restarted at the base
+    rate; manage_training now derives it from the resumed epoch, and the engine restores its own ``lr`` too)."""
+    from distributed_vgg_f_b200.cli import parse_command_line
+    from distributed_vgg_f_b200.train import manage_training
+
+    ck = str(tmp_path / "ck.pt")
+    base = ["-iu", "tcp://127.0.0.1:1", "-rn", "0", "-ws", "1", "-rd", synth_root, "-nc", "-mb", "4", "-lr", "0.01",
+            "--model", "vggf-tiny", "--engine", "oracle", "--lr-step", "1", "--lr-gamma", "0.5"]
+    first = manage_training(parse_command_line(base + ["-ep", "2", "--save", ck]))
+    assert abs(first.optimizer.param_groups[0]["lr"] - 0.01 * 0.5 ** 2) < 1e-12
+    # resume at epoch 3 of 2: nothing left to train, the optimizer shows the rate epoch 3 WOULD run at
+    resumed = manage_training(parse_command_line(base + ["-ep", "2", "--resume", ck]))
+    assert abs(resumed.optimizer.param_groups[0]["lr"] - 0.01 * 0.5 ** 2) < 1e-12
+    # a checkpoint whose stored rate was lost (older file) still resumes at the right rate
+    payload = torch.load(ck, map_location="cpu", weights_only=True)
+    for g in payload["optimizer"]["param_groups"]:
+        g["lr"] = 0.01
+    torch.save(payload, ck)
+    resumed = manage_training(parse_command_line(base + ["-ep", "2", "--resume", ck]))
+    assert abs(resumed.optimizer.param_groups[0]["lr"] - 0.01 * 0.5 ** 2) < 1e-12
