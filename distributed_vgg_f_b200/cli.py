@@ -69,7 +69,9 @@ def build_parser() -> argparse.ArgumentParser:
     ext.add_argument("--engine", default="auto", choices=["auto", "native", "oracle"],
                      help="native = sm_100a kernels; oracle = torch ops (CPU / reference numerics)")
     ext.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"],
-                     help="compute dtype of the native engine (master weights are always fp32)")
+                     help="bf16: the sm_100a engine (bf16 activations / weights / wire, fp32 master weights, moments and "
+                          "accumulators).  fp32: the reference's arithmetic on the torch-op engine (the native kernels "
+                          "have no tf32 path yet)")
     ext.add_argument("--optimizer", default="adam", choices=["adam", "sgd"])
     ext.add_argument("--momentum", type=float, default=TRAIN.momentum)
     ext.add_argument("--lr-step", type=int, default=0,
@@ -110,8 +112,10 @@ def build_parser() -> argparse.ArgumentParser:
     ext.add_argument("--class-weights", default=None,
                      help="comma-separated per-class loss weights (the reference's commented-out "
                           "CLASS_OPTIM_WEIGHTS, distributedUtil.py:27-28)")
-    ext.add_argument("--profile", default=None, choices=[None, "events", "nvtx"],
-                     help="events: per-phase CUDA-event timings each epoch; nvtx: emit NVTX ranges")
+    ext.add_argument("--profile", default=None, choices=[None, "events", "nvtx", "timeline"],
+                     help="events: per-phase CUDA-event timings each epoch; nvtx: emit NVTX ranges; timeline: print, for "
+                          "the last training step of every epoch, when each layer's kernels and each bucket's reduction / "
+                          "update finished (CUDA events, ms since the start of the step; native engine)")
     ext.add_argument("--log-jsonl", default=None, help="append one JSON record per epoch")
     return parser
 

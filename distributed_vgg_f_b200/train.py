@@ -33,6 +33,14 @@ def _want_native(args, device: torch.device) -> bool:
     native_ok = device.type == "cuda" and torch.cuda.get_device_capability(device)[0] >= 10
     if args.engine == "native" and not native_ok:
         raise RuntimeError("--engine native needs an sm_100 GPU (got %s)" % device)
+    if native_ok and getattr(args, "dtype", "bf16") == "fp32":
+        # The sm_100a kernels compute in bf16 (fp32 master weights, moments and accumulators).  The reference's
+        # fp32 arithmetic (distributedVggf.py:162-172) is served by the torch-op engine -- same model, same
+        # bucketed gradient averaging (FlatDDP) -- until a tcgen05 kind::tf32 path exists.
+        if args.engine == "native":
+            raise RuntimeError("--engine native computes in bf16; --dtype fp32 runs on --engine oracle (torch ops)")
+        print("[Info] --dtype fp32: using the torch-op engine (the native kernels compute in bf16)", flush=True)
+        return False
     return native_ok
 
 
@@ -137,6 +145,9 @@ def manage_training(args) -> Trainer:
             rec = dict(trainer.history[-1], time=time.time(), world_size=args.world_size)
             if hasattr(model, "phase_times"):
                 rec["phase_ms"] = model.phase_times()
+            for key in ("epoch_host_times", "epoch_allreduce"):       # set by Trainer for native engines
+                if getattr(trainer, key, None):
+                    rec[key[len("epoch_"):]] = getattr(trainer, key)
             with open(args.log_jsonl, "a") as f:
                 f.write(json.dumps(rec) + "\n")
 
@@ -147,6 +158,7 @@ def manage_training(args) -> Trainer:
             raise ValueError("--class-weights needs %d comma-separated values" % num_classes)
     trainer = Trainer(model, optimizer, train_loader, valid_loader, device, class_weights=cw,
                       on_epoch_end=on_epoch_end, shard_eval=getattr(args, "shard_eval", False))
+    trainer.profile_timeline = getattr(args, "profile", None) == "timeline"
     if getattr(args, "eval_only", False):        # score a checkpoint: one validation pass, no training
         test_loss, test_acc = trainer._evaluate()
         print("[Info] Evaluation: test loss: {}, test acc: {}.".format(test_loss, test_acc), flush=True)

@@ -41,6 +41,11 @@ def _bf16_peak() -> float:
     return 1405.9
 
 
+def sys_stdout_flush() -> None:
+    import sys
+    sys.stdout.flush()
+
+
 def _is_native(model) -> bool:
     return hasattr(model, "train_step") and hasattr(model, "eval_step")
 
@@ -95,12 +100,29 @@ class Trainer:
             if self.on_epoch_end is not None:
                 self.on_epoch_end(epoch, self)
 
+    @staticmethod
+    def _print_timeline(rows) -> None:
+        """--profile timeline: one line per mark, compute stream first, then the side streams."""
+        if not rows:
+            return
+        print("[Timeline] last training step of the epoch, ms since its start (CUDA events)", flush=True)
+        prev = 0.0
+        for name, lane, ms in rows:
+            if lane == "compute":
+                print("[Timeline]   compute %-26s %8.3f  +%.3f" % (name, ms, ms - prev))
+                prev = ms
+        for name, lane, ms in rows:
+            if lane != "compute":
+                print("[Timeline]   %-7s %-26s %8.3f" % (lane, name, ms))
+        sys_stdout_flush()
+
     def _comm_line(self) -> str:
         """Gradient all-reduce of the epoch as the step saw it: bus GB/s and fraction of the NVLink rate
         (SURVEY 5.5).  Needs ``engine.comm_timing(True)`` (the CLI's --profile comm)."""
         rep = getattr(self.model, "comm_report", None)
         steps = len(self.train_loader) if hasattr(self.train_loader, "__len__") else 0
         r = rep(max(steps, 1)) if rep is not None else None
+        self.epoch_allreduce = r
         if not r:
             return ""
         return ", grad all-reduce {:.0f} MB/step in {:.2f} ms = {:.0f} GB/s bus ({:.0f}% of 770 measured, {:.0f}% of 900 nominal)".format(
@@ -129,12 +151,20 @@ class Trainer:
             self.model.set_meter(meter)
             t0 = time.perf_counter()
             first = None
-            for batch in self.train_loader:
+            want_tl = getattr(self, "profile_timeline", False) and hasattr(self.model, "timeline")
+            n_steps = len(self.train_loader) if hasattr(self.train_loader, "__len__") else 0
+            for k, batch in enumerate(self.train_loader):
                 if first is None:
                     first = time.perf_counter() - t0       # loader start-up: time to the first batch
+                if want_tl and k == n_steps - 1:           # trace the epoch's last step
+                    self.model.sync()
+                    self.model.timeline(True)
                 self.model.train_step(batch)
             t1 = time.perf_counter()
             self.model.sync()
+            if want_tl:
+                self._print_timeline(self.model.timeline_report())
+                self.model.timeline(False)
             self.epoch_host_times = {"first_batch_ms": 1e3 * (first or 0.0), "enqueue_ms": 1e3 * (t1 - t0),
                                      "drain_ms": 1e3 * (time.perf_counter() - t1)}
             return meter.snapshot()

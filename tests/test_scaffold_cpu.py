@@ -623,3 +623,54 @@ def test_resume_behind_an_lr_step_boundary_keeps_the_decayed_rate(synth_root, tm
     torch.save(payload, ck)
     resumed = manage_training(parse_command_line(base + ["-ep", "2", "--resume", ck]))
     assert abs(resumed.optimizer.param_groups[0]["lr"] - 0.01 * 0.5 ** 2) < 1e-12
+
+
+def test_trainer_perf_lines_with_a_native_style_engine(capsys):
+    """Trainer's observability for engines that own the whole step (NativeEngine's surface, stubbed on the CPU):
+    [Perf] throughput + gradient all-reduce GB/s and NVLink fraction, host-side epoch timing, and
+    --profile timeline (marks of the epoch's LAST training step only)."""
+    from distributed_vgg_f_b200.trainer import Trainer
+    from distributed_vgg_f_b200.utils.metrics import DeviceMeter
+
+    class Engine:
+        def __init__(self):
+            self.meter, self.steps, self.tl_on, self.tl_steps = None, 0, False, []
+
+        def set_meter(self, m):
+            self.meter = m
+
+        def train_step(self, batch):
+            self.steps += 1
+            if self.tl_on:
+                self.tl_steps.append(self.steps)
+            self.meter.buf += torch.tensor([0.5 * 4, 3.0, 4.0, 0.0])
+
+        def eval_step(self, batch):
+            self.meter.buf += torch.tensor([0.25 * 4, 4.0, 4.0, 0.0])
+
+        def sync(self):
+            pass
+
+        def timeline(self, on):
+            self.tl_on = on
+
+        def timeline_report(self):
+            return [("step start", "compute", 0.0), ("bwd features.0", "compute", 6.5), ("ar23 end", "comm", 6.6),
+                    ("opt23 end", "opt", 6.7)]
+
+        def comm_report(self, steps):
+            return {"wire_MB_per_step": 272.8, "ms_per_step": 2.5, "bus_GBs": 190.0, "frac_of_770_measured": 0.247,
+                    "frac_of_900_nominal": 0.211}
+
+    eng = Engine()
+    batches = [object()] * 5
+    tr = Trainer(eng, None, batches, batches[:2], torch.device("cpu"))
+    tr.profile_timeline = True
+    tr.fit(2)
+    out = capsys.readouterr().out
+    assert out.count("[Info] Epoch:") == 2 and "train loss: 0.500000, train acc: 75.00%" in out
+    assert "grad all-reduce 273 MB/step in 2.50 ms = 190 GB/s bus (25% of 770 measured, 21% of 900 nominal)" in out
+    assert out.count("host: first batch after") == 2 and "validation pass" in out
+    assert eng.tl_steps == [5, 10], eng.tl_steps                  # only the last step of each epoch was traced
+    assert out.count("[Timeline] last training step") == 2 and "compute bwd features.0" in out and "opt     opt23 end" in out
+    assert tr.epoch_allreduce["bus_GBs"] == 190.0 and tr.epoch_host_times["enqueue_ms"] >= 0.0
