@@ -55,6 +55,29 @@ def test_cli_two_ranks_gloo(synth_root, tmp_path):
     assert payload["epoch"] == 2 and all(k.startswith("module.") for k in payload["model"])
 
 
+@pytest.mark.skipif(os.environ.get("B200_SKIP_SLOW", "0") == "1",
+                    reason="B200_SKIP_SLOW=1: the full 136 M-parameter model on two CPU ranks takes ~40 s "
+                           "(a 2-epoch run is committed as profiles/r2_config1_cpu_gloo_full_vggf_mb16_rank*.log)")
+def test_baseline_config_1_as_written_full_vggf_mb16_ws2_gloo(tmp_path):
+    """BASELINE.json config #1 verbatim: VGG-F 3-class (the full 136 M-parameter model, not vggf-tiny),
+    synthetic 128x128 ImageFolder, DDP world_size=2 on CPU/gloo, mb=16.  Same observable as the reference run
+    recorded in SURVEY 0.2: both ranks print the identical test loss, their sharded train losses differ."""
+    port = _free_port()
+    root = str(tmp_path / "synth16")
+    procs = []
+    for r in range(2):
+        cmd = [sys.executable, "-m", "distributed_vgg_f_b200", "-iu", "tcp://127.0.0.1:%d" % port, "-rn", str(r), "-ws", "2",
+               "-rd", root, "-ep", "1", "-lr", "0.00001", "-mb", "16", "-nc", "--synthetic", "16"]
+        procs.append(subprocess.Popen(cmd, cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT), stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=3000)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    pat = re.compile(r"train loss: ([\d.]+), train acc: [\d.]+%, test loss: ([\d.]+), test acc: ([\d.]+)%")
+    a, b = (pat.search(o).groups() for o in outs)
+    assert a[1] == b[1] and a[2] == b[2] and a[0] != b[0], (a, b)
+    assert all("model='vggf'" in o and "mini_batch=16" in o and "world_size=2" in o for o in outs)
+
+
 def _ddp_worker(rank, world, port, root):
     import torch.distributed as dist
 
