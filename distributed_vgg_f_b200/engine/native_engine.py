@@ -32,7 +32,7 @@ from ..config import DATA, TRAIN
 from ..data.loader import FusedBatch
 from ..models import layout as L
 from ..models.vggf import VGGSpec, build_oracle
-from ..parallel.buckets import BucketPlan, make_bucket_plan
+from ..parallel.buckets import BucketPlan, engine_bucket_plan
 from ..parallel.process_group import distributed_is_initialized
 from ..utils.metrics import DeviceMeter
 
@@ -122,12 +122,7 @@ class NativeEngine:
         # FC weights (ready first, 88 % of the bytes): ``bucket_mb`` messages.  Convolution gradients
         # (ready one layer at a time over the rest of backward): one bucket per big layer, and a small
         # final bucket -- its reduction and update are the only exposed part of the exchange.
-        cap = int(bucket_mb * 1024 * 1024 / 4)
-        order = L.ready_order(spec)
-        first_conv = next((n for n, _ in order if n.startswith("features.")), "")
-        self.plan: BucketPlan = make_bucket_plan(
-            order, cap_elems=cap, late_cap_elems=min(cap, int(conv_bucket_mb * 1024 * 1024 / 4)),
-            late_from=first_conv, tail_elems=int(tail_bucket_kb * 1024 / 4))
+        self.plan: BucketPlan = engine_bucket_plan(L.ready_order(spec), bucket_mb, conv_bucket_mb, tail_bucket_kb)
         n = self.plan.total
         self.p32 = torch.zeros(n, dtype=F32, device=dev)
         self.g32 = torch.zeros(n, dtype=F32, device=dev)

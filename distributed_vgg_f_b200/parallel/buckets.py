@@ -116,3 +116,14 @@ def make_bucket_plan(ready_order: Sequence[Tuple[str, int]], cap_elems: int = 16
         cur_names.append(name)
     close(total)
     return BucketPlan(offsets, numels, order, total, buckets, align)
+
+
+def engine_bucket_plan(ready_order: Sequence[Tuple[str, int]], bucket_mb: float = 32.0, conv_bucket_mb: float = 9.5,
+                       tail_bucket_kb: float = 2400.0) -> BucketPlan:
+    """The plan NativeEngine uses (sizes in MB / KB of fp32 gradient): ``bucket_mb`` messages for the FC weights
+    that are ready first, ``conv_bucket_mb`` (one big conv layer) from the first ``features.*`` tensor on, and a
+    final bucket of at most ``tail_bucket_kb``.  Also what ``python -m distributed_vgg_f_b200.tools.plan`` prints."""
+    cap = int(bucket_mb * 1024 * 1024 / 4)
+    first_conv = next((n for n, _ in ready_order if n.startswith("features.")), "")
+    return make_bucket_plan(ready_order, cap_elems=cap, late_cap_elems=min(cap, int(conv_bucket_mb * 1024 * 1024 / 4)),
+                            late_from=first_conv, tail_elems=int(tail_bucket_kb * 1024 / 4))

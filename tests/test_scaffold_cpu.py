@@ -674,3 +674,31 @@ def test_trainer_perf_lines_with_a_native_style_engine(capsys):
     assert eng.tl_steps == [5, 10], eng.tl_steps                  # only the last step of each epoch was traced
     assert out.count("[Timeline] last training step") == 2 and "compute bwd features.0" in out and "opt     opt23 end" in out
     assert tr.epoch_allreduce["bus_GBs"] == 190.0 and tr.epoch_host_times["enqueue_ms"] >= 0.0
+
+
+def test_plan_tool_and_engine_bucket_plan(capsys):
+    """tools/plan prints what NativeEngine executes: the same plan object (engine_bucket_plan), the ZeRO-1 / all-reduce
+    split by world size, NVLS vs the no-multicast fallback."""
+    from distributed_vgg_f_b200.models import layout as L
+    from distributed_vgg_f_b200.parallel.buckets import engine_bucket_plan
+    from distributed_vgg_f_b200.tools import plan as P
+
+    spec = vggf_spec(3)
+    order = L.ready_order(spec)
+    first_conv = next(n for n, _ in order if n.startswith("features."))
+    a = engine_bucket_plan(order)
+    b = make_bucket_plan(order, cap_elems=8 * 1024 * 1024, late_cap_elems=int(9.5 * 1024 * 1024 / 4),
+                         late_from=first_conv, tail_elems=int(2400 * 1024 / 4))
+    assert [(x.start, x.end, x.tensors) for x in a.buckets] == [(x.start, x.end, x.tensors) for x in b.buckets]
+    _, rows8 = P.describe("vggf", 3, world=8)
+    _, rows2 = P.describe("vggf", 3, world=2)
+    _, rows8_nomc = P.describe("vggf", 3, world=8, multicast=False)
+    z8 = [r for r in rows8 if r[6].startswith("zero1")]
+    assert len(z8) == 15 and all(r[4] in ("classifier.0.weight", "classifier.3.weight") for r in z8)
+    assert sum(r[1] for r in z8) / sum(r[1] for r in rows8) > 0.85           # 88 % of the elements
+    assert not any(r[6].startswith("zero1") for r in rows2)                  # auto: from 4 ranks
+    assert all("nvls" in r[6] for r in rows8) and not any("nvls" in r[6] for r in rows8_nomc)
+    assert "oneshot" in [r for r in rows8_nomc if r[4] == "classifier.0.bias"][0][6]
+    assert P.main(["--world", "4"]) == 0
+    out = capsys.readouterr().out
+    assert "24 buckets" in out and "272.8 MB of bf16 wire per step" in out and "features.0.weight" in out
